@@ -1,0 +1,108 @@
+"""Generates the golden fixtures under tests/golden/ by running THE REFERENCE ITSELF
+(oracle/_ref/ref_harness, built from /root/reference by `make -C oracle ref`).
+
+Run here (the container that has /root/reference); the fixtures are committed so that the
+GPU box, which has no reference tree, can still check the oracle port and the CUDA path.
+
+    python tests/golden/make_golden.py
+
+Writes:
+  scenes/<name>.fscene.gz   flat scene dumped by the reference's own loader (Application::load ->
+                            get_static_scene -> build_accel primitive order)
+  <name>.units.npz          ray batch + BVHAccel::intersect hits; BSDF f / sample_pdf batch;
+                            light contain_point / sample_pdf batch; camera generate_ray /
+                            sample_ray_pdf batch (480x360)
+  <name>.render.npz         reference `-t 1` render (fp64 sum / eye / light buffers, ray count)
+  CBspheres_lambertian.strategies.npz   reference per-(t,s) images (debug filter of bidirection.cpp:492-493)
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "bidirectional-pathtracing_b200"))
+from bdpt import flatscene as fs  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+# name -> (render W, H, ns, m)
+SCENES = {
+    "CBspheres_lambertian": (64, 48, 2, 5),
+    "CBspheres": (64, 48, 2, 5),
+    "CBgems": (48, 36, 1, 16),
+    "CBspheres_lambertian_occluded": (48, 36, 2, 4),
+    "CBempty": (40, 30, 2, 3),
+    "CBbunny": (40, 30, 1, 5),
+    "CBcoil": (40, 30, 1, 5),
+}
+
+
+def unit(v):
+    return v / np.linalg.norm(v, axis=-1, keepdims=True)
+
+
+def ray_batch(sc, rng, n):
+    """Interior random rays, primary-like rays from the camera, and short shadow-like segments."""
+    lo, hi = np.array([-1.0, 0.0, -1.0]), np.array([1.0, 1.5, 1.0])
+    k = n // 3
+    o1 = rng.uniform(lo, hi, (k, 3)); d1 = unit(rng.normal(size=(k, 3)))
+    r1 = np.concatenate([o1, d1, np.full((k, 1), float(np.float32(1e-5))), np.full((k, 1), np.inf)], 1)
+    cam = sc.camera[0]
+    tgt = rng.uniform(lo, hi, (k, 3)); o2 = np.broadcast_to(cam["pos"], (k, 3)); d2 = unit(tgt - o2)
+    r2 = np.concatenate([o2, d2, np.full((k, 1), cam["nclip"]), np.full((k, 1), cam["fclip"])], 1)
+    a = rng.uniform(lo, hi, (n - 2 * k, 3)); b = rng.uniform(lo, hi, (n - 2 * k, 3))
+    dist = np.linalg.norm(b - a, axis=1, keepdims=True)
+    r3 = np.concatenate([a, (b - a) / dist, np.full_like(dist, float(np.float32(1e-5))), dist - float(np.float32(1e-5))], 1)
+    return np.concatenate([r1, r2, r3], 0)
+
+
+def main():
+    assert O.have_ref(), "build the reference first: make -C oracle ref"
+    os.makedirs(os.path.join(OUT, "scenes"), exist_ok=True)
+    for name, (W, H, ns, m) in SCENES.items():
+        dae = O.ref_scene(name)
+        tmp = os.path.join(OUT, "scenes", name + ".fscene")
+        O.ref_dump(dae, tmp)
+        sc = fs.load(tmp)
+        os.remove(tmp)
+        sc.save(os.path.join(OUT, "scenes", name + ".fscene.gz"))
+        rng = np.random.default_rng(sum(map(ord, name)))
+        big = sc.n_prims > 1000
+        rays = ray_batch(sc, rng, 3000 if not big else 6000)
+        hits = O.ref_batch("intersect", dae, rays, 8, 6)
+        M = 600
+        bq = np.zeros((M, 7)); bq[:, 0] = rng.integers(0, len(sc.materials), M)
+        bq[:, 1:4] = unit(rng.normal(size=(M, 3))); bq[:, 4:7] = unit(rng.normal(size=(M, 3)))
+        bout = O.ref_batch("bsdf", dae, bq, 7, 8)
+        lq = np.zeros((M, 7)); lq[:, 0] = rng.integers(0, len(sc.lights), M)
+        lq[:, 1:4] = rng.uniform([-1, 0, -1], [1, 1.5, 1], (M, 3))
+        on = sc.lights["position"][lq[: M // 2, 0].astype(int)]
+        lq[: M // 2, 2] = on[:, 1]  # on the light's plane (scenes are Y-up, lights face -Y)
+        lq[:, 4:7] = unit(rng.normal(size=(M, 3)))
+        lout = O.ref_batch("light", dae, lq, 7, 6)
+        cq = np.zeros((M, 5)); cq[:, 0:2] = rng.uniform(0, 1, (M, 2)); cq[:, 2:5] = rng.uniform([-1, 0, -1], [1, 1.5, 1], (M, 3))
+        cout = O.ref_batch("camera", dae, cq, 5, 11, extra=(480, 360))
+        np.savez_compressed(os.path.join(OUT, name + ".units.npz"), rays=rays, hits=hits, bsdf_in=bq, bsdf_out=bout,
+                            light_in=lq, light_out=lout, cam_in=cq, cam_out=cout, cam_wh=np.array([480, 360]))
+        s, e, l, info = O.ref_render(dae, W, H, ns, m, threads=1)
+        np.savez_compressed(os.path.join(OUT, name + ".render.npz"), sum=s, eye=e, light=l,
+                            params=np.array([W, H, ns, m]), rays=np.array([info["rays"]]))
+        print(name, "prims", sc.n_prims, "render rays", info["rays"])
+
+    # per-strategy images, small
+    name, (W, H, ns, m) = "CBspheres_lambertian", (32, 24, 2, 3)
+    dae = O.ref_scene(name)
+    out = {}
+    for t in range(1, m + 2):
+        for s_ in range(0, m + 2):
+            s, e, l, info = O.ref_render(dae, W, H, ns, m, threads=1, strategy=(t, s_))
+            out[f"sum_t{t}_s{s_}"] = s
+    np.savez_compressed(os.path.join(OUT, name + ".strategies.npz"), params=np.array([W, H, ns, m]), **out)
+    print("strategies done")
+
+
+if __name__ == "__main__":
+    main()
