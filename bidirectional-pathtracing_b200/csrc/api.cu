@@ -1,0 +1,655 @@
+// api.cu — the C-ABI of libbdpt_b200.so (include/bdpt_b200.h): context, scene upload (host BVH
+// build + fp32 narrowing), batch scheduling of the three wavefront kernels, frame buffers, stats
+// and the parity test hooks.  No CPU fallback: without a CUDA device every call fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bdpt_b200.h"
+#include "bvh8.h"
+#include "kernels.cuh"
+
+using namespace bdpt;
+
+namespace {
+thread_local std::string g_create_error = "";
+}
+
+struct BdptContext {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+
+  // scene
+  bool have_scene = false;
+  BdptCamera cam_base{};
+  DScene sc{};
+  uint4* d_nodes = nullptr;
+  float4 *d_prims = nullptr, *d_shading = nullptr, *d_mats = nullptr, *d_lights = nullptr;
+  uint32_t bvh_nodes = 0, bvh_depth = 0;
+  double ms_bvh_build = 0;
+
+  // frame
+  int W = 0, H = 0;
+  DCamera cam{};
+  float *acc_eye = nullptr, *acc_light = nullptr, *resolve_tmp = nullptr;
+  uint8_t* rgba_tmp = nullptr;
+  int ns_last = 1;
+
+  // batch storage
+  size_t cap_B = 0; int cap_m = -1; size_t cap_q = 0;
+  float4 *v0 = nullptr, *v1 = nullptr, *v2 = nullptr, *v3 = nullptr, *q0 = nullptr, *q1 = nullptr, *q2 = nullptr;
+  int* counts = nullptr;
+  unsigned int* qctr = nullptr;
+  unsigned long long* d_stats = nullptr;
+  unsigned int* h_qctr = nullptr;  // pinned
+
+  // stats
+  BdptStats stats{};
+  std::vector<cudaEvent_t> ev;
+  int sm_count = 148;
+};
+
+namespace {
+
+#define CK(call)                                                                   \
+  do {                                                                             \
+    cudaError_t e_ = (call);                                                       \
+    if (e_ != cudaSuccess) {                                                       \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);              \
+      return BDPT_ERR_CUDA;                                                        \
+    }                                                                              \
+  } while (0)
+
+int fail(BdptContext* ctx, int code, const std::string& msg) { ctx->err = msg; return code; }
+
+template <class T>
+void dfree(T*& p) { if (p) { cudaFree(p); p = nullptr; } }
+
+float ibits(int i) { float f; memcpy(&f, &i, 4); return f; }
+float f_down(double v) { float f = (float)v; if ((double)f > v) f = std::nextafterf(f, -INFINITY); return f; }
+float f_up(double v) { float f = (float)v; if ((double)f < v) f = std::nextafterf(f, INFINITY); return f; }
+
+void inverse3(const double* c, double* r /* rows of the inverse */) {
+  // c: three column vectors
+  const double *a = c, *b = c + 3, *cc = c + 6;
+  double r0[3] = {b[1] * cc[2] - b[2] * cc[1], b[2] * cc[0] - b[0] * cc[2], b[0] * cc[1] - b[1] * cc[0]};
+  double r1[3] = {cc[1] * a[2] - cc[2] * a[1], cc[2] * a[0] - cc[0] * a[2], cc[0] * a[1] - cc[1] * a[0]};
+  double r2[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+  double det = a[0] * r0[0] + a[1] * r0[1] + a[2] * r0[2];
+  for (int k = 0; k < 3; k++) { r[k] = r0[k] / det; r[3 + k] = r1[k] / det; r[6 + k] = r2[k] / det; }
+}
+
+void make_dcamera(const BdptCamera& c, int W, int H, DCamera* out) {
+  const double PI = 3.14159265358979323;
+  double hfov = c.hfov_deg, vfov = c.vfov_deg;
+  if (W != (int)c.screen_w || H != (int)c.screen_h) {
+    // Camera::set_screen_size, reference camera.cpp:83-89
+    hfov = 2 * (std::atan(((double)W) / (2 * c.screen_dist)) * (180 / PI));
+    vfov = 2 * (std::atan(((double)H) / (2 * c.screen_dist)) * (180 / PI));
+  }
+  out->pos = mk3((float)c.pos[0], (float)c.pos[1], (float)c.pos[2]);
+  out->c2w_x = mk3((float)c.c2w[0], (float)c.c2w[1], (float)c.c2w[2]);
+  out->c2w_y = mk3((float)c.c2w[3], (float)c.c2w[4], (float)c.c2w[5]);
+  out->c2w_z = mk3((float)c.c2w[6], (float)c.c2w[7], (float)c.c2w[8]);
+  double inv[9];
+  inverse3(c.c2w, inv);
+  out->w2c_r0 = mk3((float)inv[0], (float)inv[1], (float)inv[2]);
+  out->w2c_r1 = mk3((float)inv[3], (float)inv[4], (float)inv[5]);
+  out->w2c_r2 = mk3((float)inv[6], (float)inv[7], (float)inv[8]);
+  out->tan_h = (float)std::tan(hfov * PI / 360);
+  out->tan_v = (float)std::tan(vfov * PI / 360);
+  out->nclip = (float)c.nclip; out->fclip = (float)c.fclip;
+  out->W = W; out->H = H;
+}
+
+int ensure_batch_storage(BdptContext* ctx, size_t B, int m, size_t qcap) {
+  if (B > ctx->cap_B || m > ctx->cap_m) {
+    dfree(ctx->v0); dfree(ctx->v1); dfree(ctx->v2); dfree(ctx->v3); dfree(ctx->counts);
+    size_t nB = std::max(B, ctx->cap_B); int nm = std::max(m, ctx->cap_m);
+    size_t n = 2 * (size_t)(nm + 1) * nB;
+    CK(cudaMalloc(&ctx->v0, n * sizeof(float4))); CK(cudaMalloc(&ctx->v1, n * sizeof(float4)));
+    CK(cudaMalloc(&ctx->v2, n * sizeof(float4))); CK(cudaMalloc(&ctx->v3, n * sizeof(float4)));
+    CK(cudaMalloc(&ctx->counts, 2 * nB * sizeof(int)));
+    ctx->cap_B = nB; ctx->cap_m = nm;
+  }
+  if (qcap > ctx->cap_q) {
+    dfree(ctx->q0); dfree(ctx->q1); dfree(ctx->q2);
+    CK(cudaMalloc(&ctx->q0, qcap * sizeof(float4))); CK(cudaMalloc(&ctx->q1, qcap * sizeof(float4)));
+    CK(cudaMalloc(&ctx->q2, qcap * sizeof(float4)));
+    ctx->cap_q = qcap;
+  }
+  if (!ctx->qctr) {
+    CK(cudaMalloc(&ctx->qctr, 4 * sizeof(unsigned int)));
+    CK(cudaMalloc(&ctx->d_stats, 4 * sizeof(unsigned long long)));
+    CK(cudaMemset(ctx->d_stats, 0, 4 * sizeof(unsigned long long)));
+    CK(cudaMallocHost(&ctx->h_qctr, 4 * sizeof(unsigned int)));
+  }
+  return BDPT_OK;
+}
+
+cudaEvent_t get_event(BdptContext* ctx, size_t i) {
+  while (ctx->ev.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev.push_back(e); }
+  return ctx->ev[i];
+}
+
+void fill_job(BdptContext* ctx, const BdptRenderParams* p, Job* J) {
+  memset(J, 0, sizeof(Job));
+  J->sc = ctx->sc; J->cam = ctx->cam;
+  J->v0 = ctx->v0; J->v1 = ctx->v1; J->v2 = ctx->v2; J->v3 = ctx->v3; J->counts = ctx->counts;
+  J->q0 = ctx->q0; J->q1 = ctx->q1; J->q2 = ctx->q2; J->qctr = ctx->qctr; J->qcap = (unsigned int)ctx->cap_q;
+  J->acc_eye = ctx->acc_eye; J->acc_light = ctx->acc_light; J->stats = ctx->d_stats; J->dbg = nullptr;
+  J->seed = p->seed; J->m = p->max_ray_depth; J->first_sample = p->first_sample;
+  J->tiles_x = (ctx->W + 7) / 8;
+  J->npix_pad = J->tiles_x * ((ctx->H + 3) / 4) * 32;
+  J->roulette = (p->flags & BDPT_FLAG_ROULETTE) ? 1 : 0;
+  J->only_t = p->only_t; J->only_s = p->only_s;
+  J->single_x = -1; J->single_y = -1;
+}
+
+// Runs one batch on ctx->stream.  evbase >= 0: record 4 events around the three kernels.
+template <bool TRACE>
+int run_batch(BdptContext* ctx, Job& J, long evbase) {
+  CK(cudaMemsetAsync(ctx->qctr, 0, 4 * sizeof(unsigned int), ctx->stream));
+  const int threads = 128;
+  if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 0), ctx->stream);
+  k_walk<<<(2 * J.B + threads - 1) / threads, threads, 0, ctx->stream>>>(J);
+  if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 1), ctx->stream);
+  dim3 grid((J.B + threads - 1) / threads, J.m + 1);
+  k_connect<TRACE><<<grid, threads, 0, ctx->stream>>>(J);
+  if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 2), ctx->stream);
+  k_shadow<<<ctx->sm_count * 8, threads, 0, ctx->stream>>>(J);
+  if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 3), ctx->stream);
+  ctx->stats.kernel_launches += 3;
+  CK(cudaGetLastError());
+  return BDPT_OK;
+}
+
+int check_ready(BdptContext* ctx, bool need_frame) {
+  if (!ctx) return BDPT_ERR_ARG;
+  if (!ctx->have_scene) return fail(ctx, BDPT_ERR_ARG, "no scene uploaded (bdpt_upload_scene)");
+  if (need_frame && (ctx->W <= 0 || ctx->H <= 0)) return fail(ctx, BDPT_ERR_ARG, "no frame size set (bdpt_set_frame)");
+  return BDPT_OK;
+}
+
+// generic "host doubles in -> float kernel -> host doubles out" helper for the test hooks
+template <class Launch>
+int run_hook(BdptContext* ctx, const double* in, size_t n, int n_in, double* out, int n_out, Launch launch) {
+  if (n == 0) return BDPT_OK;
+  std::vector<float> hin(n * n_in), hout(n * n_out);
+  for (size_t i = 0; i < n * (size_t)n_in; i++) hin[i] = (float)in[i];
+  float *din = nullptr, *dout = nullptr;
+  CK(cudaMalloc(&din, hin.size() * sizeof(float)));
+  CK(cudaMalloc(&dout, hout.size() * sizeof(float)));
+  CK(cudaMemcpyAsync(din, hin.data(), hin.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  launch(din, dout);
+  ctx->stats.kernel_launches += 1;
+  cudaError_t e = cudaMemcpyAsync(hout.data(), dout, hout.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(din); cudaFree(dout);
+  if (e != cudaSuccess) return fail(ctx, BDPT_ERR_CUDA, cudaGetErrorString(e));
+  for (size_t i = 0; i < hout.size(); i++) out[i] = (double)hout[i];
+  return BDPT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bdpt_create(int device, BdptContext** out) {
+  if (!out) return BDPT_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                     " (libbdpt_b200 has no CPU fallback)";
+    return BDPT_ERR_CUDA;
+  }
+  if (device < 0 || device >= n) { g_create_error = "bad device index"; return BDPT_ERR_ARG; }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return BDPT_ERR_CUDA; }
+  BdptContext* ctx = new BdptContext();
+  ctx->device = device;
+  e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return BDPT_ERR_CUDA; }
+  ctx->own_stream = true;
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  *out = ctx;
+  return BDPT_OK;
+}
+
+void bdpt_destroy(BdptContext* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  dfree(ctx->d_nodes); dfree(ctx->d_prims); dfree(ctx->d_shading); dfree(ctx->d_mats); dfree(ctx->d_lights);
+  dfree(ctx->acc_eye); dfree(ctx->acc_light); dfree(ctx->resolve_tmp); dfree(ctx->rgba_tmp);
+  dfree(ctx->v0); dfree(ctx->v1); dfree(ctx->v2); dfree(ctx->v3); dfree(ctx->counts);
+  dfree(ctx->q0); dfree(ctx->q1); dfree(ctx->q2); dfree(ctx->qctr); dfree(ctx->d_stats);
+  if (ctx->h_qctr) cudaFreeHost(ctx->h_qctr);
+  for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* bdpt_last_error(const BdptContext* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int bdpt_set_stream(BdptContext* ctx, void* cuda_stream) {
+  if (!ctx) return BDPT_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)cuda_stream;
+  ctx->own_stream = false;
+  return BDPT_OK;
+}
+
+int bdpt_upload_scene(BdptContext* ctx, const BdptCamera* camera, const BdptMaterial* materials, uint32_t n_materials,
+                      const BdptLight* lights, uint32_t n_lights, const BdptPrim* prims, uint32_t n_prims) {
+  if (!ctx || !camera || (!materials && n_materials) || (!lights && n_lights) || (!prims && n_prims)) return BDPT_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (n_lights == 0) return fail(ctx, BDPT_ERR_SCENE, "scene has no light: BDPT needs at least one (bidirection.cpp:109)");
+  for (uint32_t i = 0; i < n_lights; i++)
+    if (lights[i].type != BDPT_LIGHT_AREA && lights[i].type != BDPT_LIGHT_POINT)
+      return fail(ctx, BDPT_ERR_SCENE, "light type not supported by BDPT (only area and point lights implement sample_Le, light.cpp)");
+  for (uint32_t i = 0; i < n_materials; i++)
+    if (materials[i].type < BDPT_MAT_DIFFUSE || materials[i].type > BDPT_MAT_MICROFACET)
+      return fail(ctx, BDPT_ERR_SCENE, "unknown material type");
+  for (uint32_t i = 0; i < n_prims; i++) {
+    if (prims[i].material < 0 || (uint32_t)prims[i].material >= n_materials) return fail(ctx, BDPT_ERR_SCENE, "primitive references a missing material");
+    if (prims[i].type != BDPT_PRIM_TRIANGLE && prims[i].type != BDPT_PRIM_SPHERE) return fail(ctx, BDPT_ERR_SCENE, "unknown primitive type");
+  }
+
+  auto t0 = std::chrono::steady_clock::now();
+  std::vector<BuildPrim> bp(n_prims);
+  for (uint32_t i = 0; i < n_prims; i++) {
+    const double* d = prims[i].data;
+    if (prims[i].type == BDPT_PRIM_TRIANGLE) {
+      for (int a = 0; a < 3; a++) {
+        float v0 = (float)d[a], v1 = (float)d[3 + a], v2 = (float)d[6 + a];  // the fp32 triangle the kernel tests
+        bp[i].lo[a] = std::min(v0, std::min(v1, v2));
+        bp[i].hi[a] = std::max(v0, std::max(v1, v2));
+      }
+    } else {
+      double r = std::fabs(d[3]) * (1.0 + 1e-6) + 1e-7;
+      for (int a = 0; a < 3; a++) { bp[i].lo[a] = f_down(d[a] - r); bp[i].hi[a] = f_up(d[a] + r); }
+    }
+  }
+  Bvh8 bvh;
+  build_bvh8(bp, &bvh);
+  ctx->ms_bvh_build = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (bvh.max_depth >= BDPT_STACK) return fail(ctx, BDPT_ERR_SCENE, "BVH deeper than the traversal stack");
+
+  // leaf-ordered primitive + shading records
+  std::vector<float4> hp(3 * (size_t)std::max<uint32_t>(n_prims, 1)), hs(3 * (size_t)std::max<uint32_t>(n_prims, 1));
+  for (size_t k = 0; k < bvh.prim_order.size(); k++) {
+    uint32_t id = bvh.prim_order[k];
+    const BdptPrim& p = prims[id];
+    const double* d = p.data;
+    if (p.type == BDPT_PRIM_TRIANGLE) {
+      float v0[3], v1[3], v2[3];
+      for (int a = 0; a < 3; a++) { v0[a] = (float)d[a]; v1[a] = (float)d[3 + a]; v2[a] = (float)d[6 + a]; }
+      hp[3 * k + 0] = make_float4(v0[0], v0[1], v0[2], ibits((int)id));
+      hp[3 * k + 1] = make_float4(v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2], ibits(p.material));
+      hp[3 * k + 2] = make_float4(v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2], 0.f);
+      hs[3 * k + 0] = make_float4((float)d[9], (float)d[10], (float)d[11], 0.f);
+      hs[3 * k + 1] = make_float4((float)d[12], (float)d[13], (float)d[14], 0.f);
+      hs[3 * k + 2] = make_float4((float)d[15], (float)d[16], (float)d[17], 0.f);
+    } else {
+      float r = (float)d[3];
+      hp[3 * k + 0] = make_float4((float)d[0], (float)d[1], (float)d[2], ibits((int)id));
+      hp[3 * k + 1] = make_float4(r, (float)(d[3] * d[3]), 0.f, ibits(p.material | (int)0x80000000));
+      hp[3 * k + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+      hs[3 * k + 0] = hs[3 * k + 1] = hs[3 * k + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  std::vector<float4> hm(5 * (size_t)std::max<uint32_t>(n_materials, 1));
+  for (uint32_t i = 0; i < n_materials; i++) {
+    const BdptMaterial& m = materials[i];
+    hm[5 * i + 0] = make_float4((float)m.reflectance[0], (float)m.reflectance[1], (float)m.reflectance[2], ibits(m.type));
+    hm[5 * i + 1] = make_float4((float)m.transmittance[0], (float)m.transmittance[1], (float)m.transmittance[2], (float)m.ior);
+    hm[5 * i + 2] = make_float4((float)m.radiance[0], (float)m.radiance[1], (float)m.radiance[2], (float)m.alpha);
+    hm[5 * i + 3] = make_float4((float)m.eta[0], (float)m.eta[1], (float)m.eta[2], 0.f);
+    hm[5 * i + 4] = make_float4((float)m.k[0], (float)m.k[1], (float)m.k[2], 0.f);
+  }
+  std::vector<float4> hl(5 * (size_t)n_lights);
+  for (uint32_t i = 0; i < n_lights; i++) {
+    const BdptLight& l = lights[i];
+    double nx = std::sqrt(l.dim_x[0] * l.dim_x[0] + l.dim_x[1] * l.dim_x[1] + l.dim_x[2] * l.dim_x[2]);
+    double ny = std::sqrt(l.dim_y[0] * l.dim_y[0] + l.dim_y[1] * l.dim_y[1] + l.dim_y[2] * l.dim_y[2]);
+    hl[5 * i + 0] = make_float4((float)l.radiance[0], (float)l.radiance[1], (float)l.radiance[2], ibits(l.type));
+    hl[5 * i + 1] = make_float4((float)l.position[0], (float)l.position[1], (float)l.position[2], (float)(nx * ny));  // light.cpp:199-203
+    hl[5 * i + 2] = make_float4((float)l.direction[0], (float)l.direction[1], (float)l.direction[2], 0.f);
+    hl[5 * i + 3] = make_float4((float)l.dim_x[0], (float)l.dim_x[1], (float)l.dim_x[2], 0.f);
+    hl[5 * i + 4] = make_float4((float)l.dim_y[0], (float)l.dim_y[1], (float)l.dim_y[2], 0.f);
+  }
+
+  CK(cudaStreamSynchronize(ctx->stream));
+  dfree(ctx->d_nodes); dfree(ctx->d_prims); dfree(ctx->d_shading); dfree(ctx->d_mats); dfree(ctx->d_lights);
+  CK(cudaMalloc(&ctx->d_nodes, bvh.nodes.size() * sizeof(uint32_t)));
+  CK(cudaMalloc(&ctx->d_prims, hp.size() * sizeof(float4)));
+  CK(cudaMalloc(&ctx->d_shading, hs.size() * sizeof(float4)));
+  CK(cudaMalloc(&ctx->d_mats, hm.size() * sizeof(float4)));
+  CK(cudaMalloc(&ctx->d_lights, hl.size() * sizeof(float4)));
+  CK(cudaMemcpyAsync(ctx->d_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_prims, hp.data(), hp.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_shading, hs.data(), hs.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_mats, hm.data(), hm.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_lights, hl.data(), hl.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+
+  ctx->sc.nodes = ctx->d_nodes; ctx->sc.prims = ctx->d_prims; ctx->sc.shading = ctx->d_shading;
+  ctx->sc.materials = ctx->d_mats; ctx->sc.lights = ctx->d_lights;
+  ctx->sc.n_lights = (int)n_lights; ctx->sc.n_materials = (int)n_materials;
+  ctx->sc.n_nodes = (int)(bvh.nodes.size() / 20); ctx->sc.n_prims = (int)n_prims;
+  ctx->bvh_nodes = (uint32_t)(bvh.nodes.size() / 20); ctx->bvh_depth = bvh.max_depth;
+  ctx->cam_base = *camera;
+  ctx->have_scene = true;
+  if (ctx->W > 0) make_dcamera(ctx->cam_base, ctx->W, ctx->H, &ctx->cam);
+  return BDPT_OK;
+}
+
+int bdpt_set_camera(BdptContext* ctx, const BdptCamera* camera) {
+  if (!ctx || !camera) return BDPT_ERR_ARG;
+  ctx->cam_base = *camera;
+  if (ctx->W > 0) make_dcamera(ctx->cam_base, ctx->W, ctx->H, &ctx->cam);
+  return BDPT_OK;
+}
+
+int bdpt_set_frame(BdptContext* ctx, int width, int height) {
+  if (!ctx || width <= 0 || height <= 0 || (long long)width * height > (1ll << 30)) return BDPT_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (width != ctx->W || height != ctx->H) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    dfree(ctx->acc_eye); dfree(ctx->acc_light); dfree(ctx->resolve_tmp); dfree(ctx->rgba_tmp);
+    size_t n = (size_t)width * height * 3;
+    CK(cudaMalloc(&ctx->acc_eye, n * sizeof(float)));
+    CK(cudaMalloc(&ctx->acc_light, n * sizeof(float)));
+    CK(cudaMalloc(&ctx->resolve_tmp, n * sizeof(float)));
+    CK(cudaMalloc(&ctx->rgba_tmp, (size_t)width * height * 4));
+    ctx->W = width; ctx->H = height;
+  }
+  make_dcamera(ctx->cam_base, ctx->W, ctx->H, &ctx->cam);
+  return bdpt_clear(ctx);
+}
+
+int bdpt_clear(BdptContext* ctx) {
+  if (!ctx) return BDPT_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->acc_eye) {
+    size_t n = (size_t)ctx->W * ctx->H * 3 * sizeof(float);
+    CK(cudaMemsetAsync(ctx->acc_eye, 0, n, ctx->stream));
+    CK(cudaMemsetAsync(ctx->acc_light, 0, n, ctx->stream));
+  }
+  if (ctx->d_stats) CK(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
+  BdptStats z{};
+  z.ms_bvh_build = ctx->ms_bvh_build; z.bvh_nodes = ctx->bvh_nodes;
+  ctx->stats = z;
+  return BDPT_OK;
+}
+
+int bdpt_render(BdptContext* ctx, const BdptRenderParams* p) {
+  int rc = check_ready(ctx, true);
+  if (rc) return rc;
+  if (!p || p->ns_total <= 0 || p->max_ray_depth < 0 || p->n_samples < 0 || p->first_sample < 0 || p->max_ray_depth > 64)
+    return fail(ctx, BDPT_ERR_ARG, "bad render parameters");
+  CK(cudaSetDevice(ctx->device));
+  ctx->ns_last = p->ns_total;
+  if (p->n_samples == 0) return BDPT_OK;
+
+  Job J;
+  // batch size: bounded by the vertex planes (64 B/vertex) and the worst-case shadow queue (48 B/entry)
+  const int m = p->max_ray_depth;
+  const size_t per_sample = (size_t)2 * (m + 1) * 64 + (size_t)(m + 1) * (m + 1) * 48 + 8;
+  size_t B = (size_t)(3ull << 30) / per_sample;
+  B = std::min<size_t>(B, 1u << 20);
+  B = std::max<size_t>(B & ~(size_t)1023, 1024);
+  const int tiles_x = (ctx->W + 7) / 8, npix_pad = tiles_x * ((ctx->H + 3) / 4) * 32;
+  const unsigned long long total = (unsigned long long)npix_pad * (unsigned long long)p->n_samples;
+  if (total < B) B = (size_t)((total + 1023) & ~1023ull);
+  const size_t qcap = B * (size_t)(m + 1) * (size_t)(m + 1);
+  rc = ensure_batch_storage(ctx, B, m, std::max<size_t>(qcap, 1024));
+  if (rc) return rc;
+  fill_job(ctx, p, &J);
+  J.B = (int)B; J.g_end = total;
+  // the planes are indexed with the job's own B and m (VSLOT), capacity may be larger
+
+  const unsigned long long n_batches = (total + B - 1) / B;
+  const long timed = (long)std::min<unsigned long long>(n_batches, 64);
+  cudaEvent_t e0 = get_event(ctx, 0), e1 = get_event(ctx, 1);
+  CK(cudaEventRecord(e0, ctx->stream));
+  for (unsigned long long b = 0; b < n_batches; b++) {
+    J.g0 = b * B;
+    rc = run_batch<false>(ctx, J, b < (unsigned long long)timed ? 2 + 4 * (long)b : -1);
+    if (rc) return rc;
+  }
+  CK(cudaMemcpyAsync(ctx->h_qctr, ctx->qctr, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaEventRecord(e1, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  ctx->stats.ms_total = ms;
+  double w = 0, c = 0, s = 0;
+  for (long b = 0; b < timed; b++) {
+    float a;
+    cudaEventElapsedTime(&a, ctx->ev[2 + 4 * b], ctx->ev[3 + 4 * b]); w += a;
+    cudaEventElapsedTime(&a, ctx->ev[3 + 4 * b], ctx->ev[4 + 4 * b]); c += a;
+    cudaEventElapsedTime(&a, ctx->ev[4 + 4 * b], ctx->ev[5 + 4 * b]); s += a;
+  }
+  ctx->stats.ms_walk = w; ctx->stats.ms_connect = c; ctx->stats.ms_shadow = s;
+  ctx->stats.timed_batches = (uint32_t)timed; ctx->stats.n_batches = (uint32_t)n_batches;
+  ctx->stats.batch_samples = (uint32_t)B;
+  ctx->stats.samples += (unsigned long long)ctx->W * ctx->H * (unsigned long long)p->n_samples;
+  if (ctx->h_qctr[2]) return fail(ctx, BDPT_ERR_OVERFLOW, "shadow queue overflow");
+  return BDPT_OK;
+}
+
+int bdpt_framebuffer_device(BdptContext* ctx, int which, void** device_ptr, size_t* n_floats) {
+  if (!ctx || !device_ptr || (which != BDPT_BUFFER_EYE && which != BDPT_BUFFER_LIGHT))
+    return ctx ? fail(ctx, BDPT_ERR_ARG, "only the eye and light accumulators exist on the device (sum = eye + light)") : BDPT_ERR_ARG;
+  if (!ctx->acc_eye) return fail(ctx, BDPT_ERR_ARG, "no frame size set");
+  *device_ptr = which == BDPT_BUFFER_EYE ? ctx->acc_eye : ctx->acc_light;
+  if (n_floats) *n_floats = (size_t)ctx->W * ctx->H * 3;
+  return BDPT_OK;
+}
+
+int bdpt_read_framebuffer(BdptContext* ctx, int which, float* rgb_out) {
+  if (!ctx || !rgb_out || which < 0 || which > 2) return BDPT_ERR_ARG;
+  if (!ctx->acc_eye) return fail(ctx, BDPT_ERR_ARG, "no frame size set");
+  CK(cudaSetDevice(ctx->device));
+  size_t n = (size_t)ctx->W * ctx->H * 3;
+  k_resolve<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->acc_eye, ctx->acc_light, which, 1.0f / (float)ctx->ns_last, n, ctx->resolve_tmp);
+  ctx->stats.kernel_launches += 1;
+  CK(cudaMemcpyAsync(rgb_out, ctx->resolve_tmp, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return BDPT_OK;
+}
+
+int bdpt_tonemap_rgba8(BdptContext* ctx, int which, uint8_t* rgba_out) {
+  if (!ctx || !rgba_out || which < 0 || which > 2) return BDPT_ERR_ARG;
+  if (!ctx->acc_eye) return fail(ctx, BDPT_ERR_ARG, "no frame size set");
+  CK(cudaSetDevice(ctx->device));
+  int n = ctx->W * ctx->H;
+  k_tonemap<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->acc_eye, ctx->acc_light, which, 1.0f / (float)ctx->ns_last, ctx->W, ctx->H, ctx->rgba_tmp);
+  ctx->stats.kernel_launches += 1;
+  CK(cudaMemcpyAsync(rgba_out, ctx->rgba_tmp, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return BDPT_OK;
+}
+
+int bdpt_get_stats(BdptContext* ctx, BdptStats* out) {
+  if (!ctx || !out) return BDPT_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->d_stats) {
+    unsigned long long h[4];
+    CK(cudaMemcpyAsync(h, ctx->d_stats, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.rays_closest = h[0]; ctx->stats.rays_shadow = h[1]; ctx->stats.connections = h[2];
+  }
+  ctx->stats.ms_bvh_build = ctx->ms_bvh_build; ctx->stats.bvh_nodes = ctx->bvh_nodes;
+  *out = ctx->stats;
+  return BDPT_OK;
+}
+
+// ------------------------------------------------------------------------------------ test hooks
+int bdpt_intersect_batch(BdptContext* ctx, const double* rays, size_t n, double* hits) {
+  int rc = check_ready(ctx, false);
+  if (rc) return rc;
+  if ((!rays || !hits) && n) return BDPT_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  DScene sc = ctx->sc; cudaStream_t st = ctx->stream;
+  rc = run_hook(ctx, rays, n, 8, hits, 6, [&](float* din, float* dout) {
+    k_intersect_batch<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(sc, din, n, dout);
+  });
+  if (rc) return rc;
+  for (size_t i = 0; i < n; i++) {  // ids travelled as int bits in a float lane
+    float a = (float)hits[6 * i], b = (float)hits[6 * i + 5];
+    int ia, ib; memcpy(&ia, &a, 4); memcpy(&ib, &b, 4);
+    if (hits[6 * i] == -1.0) { hits[6 * i + 1] = INFINITY; continue; }
+    hits[6 * i] = (double)ia; hits[6 * i + 5] = (double)ib;
+  }
+  return BDPT_OK;
+}
+
+int bdpt_occluded_batch(BdptContext* ctx, const double* rays, size_t n, int32_t* occluded) {
+  int rc = check_ready(ctx, false);
+  if (rc) return rc;
+  if ((!rays || !occluded) && n) return BDPT_ERR_ARG;
+  if (n == 0) return BDPT_OK;
+  CK(cudaSetDevice(ctx->device));
+  std::vector<float> h(n * 8);
+  for (size_t i = 0; i < n * 8; i++) h[i] = (float)rays[i];
+  float* din = nullptr; int* dout = nullptr;
+  CK(cudaMalloc(&din, h.size() * sizeof(float)));
+  CK(cudaMalloc(&dout, n * sizeof(int)));
+  CK(cudaMemcpyAsync(din, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  k_occluded_batch<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->sc, din, n, dout);
+  ctx->stats.kernel_launches += 1;
+  cudaError_t e = cudaMemcpyAsync(occluded, dout, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(din); cudaFree(dout);
+  if (e != cudaSuccess) return fail(ctx, BDPT_ERR_CUDA, cudaGetErrorString(e));
+  return BDPT_OK;
+}
+
+int bdpt_bsdf_eval_batch(BdptContext* ctx, const double* in, size_t n, double* out) {
+  int rc = check_ready(ctx, false);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  DScene sc = ctx->sc; cudaStream_t st = ctx->stream;
+  return run_hook(ctx, in, n, 7, out, 8, [&](float* din, float* dout) {
+    k_bsdf_eval<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(sc, din, n, dout);
+  });
+}
+
+int bdpt_bsdf_sample_batch(BdptContext* ctx, const double* in, size_t n, double* out) {
+  int rc = check_ready(ctx, false);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  DScene sc = ctx->sc; cudaStream_t st = ctx->stream;
+  return run_hook(ctx, in, n, 7, out, 7, [&](float* din, float* dout) {
+    k_bsdf_sample<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(sc, din, n, dout);
+  });
+}
+
+int bdpt_light_eval_batch(BdptContext* ctx, const double* in, size_t n, double* out) {
+  int rc = check_ready(ctx, false);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  DScene sc = ctx->sc; cudaStream_t st = ctx->stream;
+  return run_hook(ctx, in, n, 7, out, 6, [&](float* din, float* dout) {
+    k_light_eval<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(sc, din, n, dout);
+  });
+}
+
+int bdpt_camera_eval_batch(BdptContext* ctx, const double* in, size_t n, double* out) {
+  int rc = check_ready(ctx, true);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  DCamera cam = ctx->cam; cudaStream_t st = ctx->stream;
+  return run_hook(ctx, in, n, 5, out, 11, [&](float* din, float* dout) {
+    k_camera_eval<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(cam, din, n, dout);
+  });
+}
+
+int bdpt_trace_sample(BdptContext* ctx, const BdptRenderParams* p, int x, int y, int sample, double* out, size_t cap, size_t* n_out) {
+  int rc = check_ready(ctx, true);
+  if (rc) return rc;
+  if (!p || !out || x < 0 || y < 0 || x >= ctx->W || y >= ctx->H) return fail(ctx, BDPT_ERR_ARG, "bad trace arguments");
+  CK(cudaSetDevice(ctx->device));
+  const int m = p->max_ray_depth;
+  const size_t B = 1024;
+  rc = ensure_batch_storage(ctx, B, m, B * (size_t)(m + 1) * (size_t)(m + 1));
+  if (rc) return rc;
+  // the trace must not disturb the frame: render into scratch accumulators
+  float *se = nullptr, *sl = nullptr; double* dbg = nullptr;
+  size_t nacc = (size_t)ctx->W * ctx->H * 3 * sizeof(float);
+  size_t ndbg = (size_t)(m + 1) * (m + 2) * 8;
+  CK(cudaMalloc(&se, nacc)); CK(cudaMalloc(&sl, nacc)); CK(cudaMalloc(&dbg, ndbg * sizeof(double)));
+  CK(cudaMemsetAsync(se, 0, nacc, ctx->stream)); CK(cudaMemsetAsync(sl, 0, nacc, ctx->stream));
+  std::vector<double> hdbg(ndbg, -1.0);
+  CK(cudaMemcpyAsync(dbg, hdbg.data(), ndbg * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  BdptRenderParams q = *p;
+  q.first_sample = sample; q.n_samples = 1;
+  Job J;
+  fill_job(ctx, &q, &J);
+  J.acc_eye = se; J.acc_light = sl; J.dbg = dbg;
+  J.B = (int)B; J.g0 = 0; J.g_end = 1; J.single_x = x; J.single_y = y;
+  rc = run_batch<true>(ctx, J, -1);
+  std::vector<float4> hv[4]; std::vector<int> hc(2 * B);
+  size_t nv = 2 * (size_t)(m + 1) * B;
+  if (rc == BDPT_OK) {
+    float4* planes[4] = {ctx->v0, ctx->v1, ctx->v2, ctx->v3};
+    for (int k = 0; k < 4; k++) { hv[k].resize(nv); cudaMemcpyAsync(hv[k].data(), planes[k], nv * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream); }
+    cudaMemcpyAsync(hc.data(), ctx->counts, 2 * B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(hdbg.data(), dbg, ndbg * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  }
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(se); cudaFree(sl); cudaFree(dbg);
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(ctx, BDPT_ERR_CUDA, cudaGetErrorString(e));
+
+  std::vector<double> rec;
+  const int nE = hc[0], nL = hc[B];
+  rec.push_back(nE + 1); rec.push_back(nL + 1);
+  const double nan = NAN;
+  for (int kind = 0; kind < 2; kind++) {
+    int nk = kind == 0 ? nE : nL;
+    for (int j = 0; j <= nk; j++) {
+      double r[13];
+      for (double& v : r) v = nan;
+      if (j == 0) { r[6] = r[7] = r[8] = 1.0; r[9] = 1.0; r[10] = -1; }
+      else if (j == 1 && kind == 0) {
+        r[0] = ctx->cam_base.pos[0]; r[1] = ctx->cam_base.pos[1]; r[2] = ctx->cam_base.pos[2];
+        r[6] = r[7] = r[8] = 1.0; r[9] = 1.0; r[10] = -1; r[12] = 1.0;
+      } else {
+        size_t s = (size_t)(kind * (m + 1) + (j - 1)) * B;
+        float4 a = hv[0][s], b = hv[1][s], c = hv[2][s], d = hv[3][s];
+        int mat; memcpy(&mat, &a.w, 4);
+        r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = b.x; r[4] = b.y; r[5] = b.z;
+        r[6] = c.x; r[7] = c.y; r[8] = c.z; r[10] = mat;
+        if (j == 1) { r[9] = b.w; r[12] = d.x; }
+      }
+      rec.insert(rec.end(), r, r + 13);
+    }
+  }
+  for (int t = 1; t <= nE; t++)
+    for (int s = 0; s <= nL; s++) {
+      const double* r = &hdbg[8 * ((size_t)(t - 1) * (m + 2) + s)];
+      if (r[0] < 0) continue;
+      rec.insert(rec.end(), r, r + 8);
+    }
+  if (n_out) *n_out = rec.size();
+  memcpy(out, rec.data(), std::min(cap, rec.size()) * sizeof(double));
+  return BDPT_OK;
+}
+
+}  // extern "C"

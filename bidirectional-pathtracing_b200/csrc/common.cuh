@@ -1,0 +1,105 @@
+// common.cuh — fp32 vector helpers, constants and the device-side scene tables.
+// Written for sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bdpt {
+
+// reference CGL/include/CGL/misc.h:11-15
+#define BDPT_PI 3.14159265358979323f
+#define BDPT_INV_PI 0.318309886183790672f
+#define BDPT_EPS_F 0.00001f
+
+struct f3 {
+  float x, y, z;
+};
+
+__host__ __device__ inline f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+__host__ __device__ inline f3 mk3(float c) { return mk3(c, c, c); }
+__host__ __device__ inline f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__host__ __device__ inline f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__host__ __device__ inline f3 operator-(f3 a) { return mk3(-a.x, -a.y, -a.z); }
+__host__ __device__ inline f3 operator*(f3 a, f3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__host__ __device__ inline f3 operator*(f3 a, float c) { return mk3(a.x * c, a.y * c, a.z * c); }
+__host__ __device__ inline f3 operator*(float c, f3 a) { return mk3(a.x * c, a.y * c, a.z * c); }
+__host__ __device__ inline float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__host__ __device__ inline f3 cross(f3 u, f3 v) {
+  return mk3(u.y * v.z - u.z * v.y, u.z * v.x - u.x * v.z, u.x * v.y - u.y * v.x);
+}
+__device__ inline float norm2(f3 a) { return dot(a, a); }
+__device__ inline float norm(f3 a) { return sqrtf(dot(a, a)); }
+__device__ inline f3 normalized(f3 a) { return a * (1.0f / sqrtf(dot(a, a))); }
+__device__ inline bool is_zero(f3 a) { return a.x == 0.f && a.y == 0.f && a.z == 0.f; }
+
+// Orthonormal frame around a normal; same axis choice as the reference's make_coord_space
+// (src/pathtracer/bsdf.cpp:21-41) so that a local direction maps to the same world direction.
+struct Frame {
+  f3 x, y, z;
+  __device__ inline f3 to_world(f3 v) const { return v.x * x + v.y * y + v.z * z; }
+  __device__ inline f3 to_local(f3 v) const { return mk3(dot(x, v), dot(y, v), dot(z, v)); }
+};
+
+__device__ inline Frame make_frame(f3 n) {
+  f3 h = n;
+  float ax = fabsf(h.x), ay = fabsf(h.y), az = fabsf(h.z);
+  if (ax <= ay && ax <= az) h.x = 1.0f;
+  else if (ay <= ax && ay <= az) h.y = 1.0f;
+  else h.z = 1.0f;
+  Frame f;
+  f.z = normalized(n);
+  f.y = normalized(cross(h, f.z));
+  f.x = normalized(cross(f.z, f.y));
+  return f;
+}
+
+// ------------------------------------------------------------------ device scene tables
+// Material record: 5 x float4 (80 B), read with 16-byte loads.
+//   q0 = {reflectance.rgb, as_float(type)}
+//   q1 = {transmittance.rgb, ior}
+//   q2 = {radiance.rgb, alpha}
+//   q3 = {eta.rgb, 0}
+//   q4 = {k.rgb, 0}
+struct DMaterial {
+  float4 q[5];
+};
+
+// Light record: 6 x float4.
+//   q0 = {radiance.rgb, as_float(type)}
+//   q1 = {position.xyz, area}
+//   q2 = {direction.xyz (unit, as stored by the loader), 0}
+//   q3 = {dim_x.xyz, 0}
+//   q4 = {dim_y.xyz, 0}
+struct DLight {
+  float4 q[5];
+};
+
+struct DCamera {
+  f3 pos;
+  f3 c2w_x, c2w_y, c2w_z;  // columns of c2w
+  f3 w2c_r0, w2c_r1, w2c_r2;  // rows of w2c (= inverse of c2w)
+  float tan_h, tan_v;  // tan(hFov/2), tan(vFov/2)   (camera.cpp:200-201)
+  float nclip, fclip;
+  int W, H;
+};
+
+struct alignas(16) Node8 {  // 80 bytes, see bvh8.h
+  uint4 q[5];
+};
+
+struct DScene {
+  const uint4* nodes;       // Node8 as 5 x uint4
+  const float4* prims;      // leaf-ordered primitive records, 3 x float4 each
+  const float4* shading;    // leaf-ordered shading normals n1,n2,n3, 3 x float4 each
+  const float4* materials;  // DMaterial as 5 x float4
+  const float4* lights;     // DLight as 5 x float4
+  int n_lights;
+  int n_materials;
+  int n_nodes;
+  int n_prims;
+};
+
+__device__ inline float4 ldg4(const float4* p) { return __ldg(p); }
+__device__ inline uint4 ldg4(const uint4* p) { return __ldg(p); }
+
+}  // namespace bdpt

@@ -1,0 +1,508 @@
+// kernels.cuh — the wavefront BDPT kernels.
+//
+// One batch of B samples goes through three kernels:
+//   k_walk     one thread per subpath (B eye + B light): random walk with closest-hit traversal
+//              and BSDF sampling; writes path vertices to SoA planes in HBM
+//              (reference prepare_bidirectional_subpath + sample_light_ray, bidirection.cpp:20-118)
+//   k_connect  one thread per (sample, t): loops the light-subpath length s, evaluates the
+//              unweighted contribution and the MIS weight of strategy (s,t), and appends a shadow
+//              ray {segment, pixel, weighted contribution} to a queue with warp-aggregated atomics
+//              (reference estimate_bidirection_radiance + multiple_importance_sampling_weight,
+//              bidirection.cpp:121-469)
+//   k_shadow   persistent warps pull 32 queue entries at a time, any-hit traversal, splat the
+//              contribution if unoccluded (the reference's shadow bvh->intersect, :419-433, and
+//              update_pixel, :544-551)
+//
+// MIS in O(1) per strategy.  The reference walks both ratio chains for every strategy (O(s+t)
+// each, O(m^3) per sample).  Every factor of those chains except the one at the connection is a
+// function of one subpath alone, so k_walk caches per vertex j
+//     D_j = pdf_{j-1}(-> j) * G(j-1, j)        (the chain's denominator at j)
+//     S_j = sum_{i<=j} flag_i * prod_{l=i}^{j-1} (R_l)^2,  R_l = pdf_{l+1}(-> l) * G(l+1, l) / D_l
+// and a strategy's weight is 1 / (1 + r_t^2 S_t + r_s^2 S^L_s) with r the connection ratio.
+// Same numbers as the reference's loops (bidirection.cpp:133-221,224-289), including its quirks:
+// wo = 0 in sample_pdf (Q5), the original light vertex in the s = 1 light chain (Q4), the
+// plane-only contain_point (Q6), light_path[0].alpha = 1 for s = 0 (Q8), no t = 0 (Q9).
+#pragma once
+#include "common.cuh"
+#include "rng.cuh"
+#include "shading.cuh"
+#include "traverse.cuh"
+
+namespace bdpt {
+
+struct Job {
+  DScene sc;
+  DCamera cam;
+  // vertex planes, each [2*(m+1)][B] float4; counts [2][B]
+  float4 *v0, *v1, *v2, *v3;
+  int* counts;
+  // shadow queue, SoA float4 x 3, and its counters {n_entries, cursor, overflow, -}
+  float4 *q0, *q1, *q2;
+  unsigned int* qctr;
+  unsigned int qcap;
+  // accumulators (un-normalised), W*H*3 floats each
+  float *acc_eye, *acc_light;
+  unsigned long long* stats;  // {closest rays, shadow rays, connections}
+  double* dbg;                // trace of one sample (bdpt_trace_sample) or null
+  unsigned long long seed;
+  unsigned long long g0;      // first job-sample index of this batch
+  unsigned long long g_end;   // one past the last job-sample index of the job
+  int B;                      // samples in this batch
+  int m;                      // max_ray_depth
+  int first_sample;           // sample index of job-sample 0
+  int tiles_x, npix_pad;      // 8x4 pixel tiles per row; padded pixel count
+  int roulette;
+  int only_t, only_s;
+  int single_x, single_y;     // >= 0: the job is this one pixel (trace mode)
+};
+
+// job-sample index -> (pixel, sample number).  Consecutive indices walk an 8x4 pixel tile, so a
+// warp's 32 primary rays are neighbours.
+__device__ inline bool decode_sample(const Job& J, unsigned long long g, int* x, int* y, int* sample) {
+  if (g >= J.g_end) return false;
+  if (J.single_x >= 0) { *x = J.single_x; *y = J.single_y; *sample = J.first_sample + (int)g; return true; }
+  unsigned long long k = g / (unsigned long long)J.npix_pad;
+  int p = (int)(g - k * (unsigned long long)J.npix_pad);
+  int tile = p >> 5, w = p & 31;
+  int tx = tile % J.tiles_x, ty = tile / J.tiles_x;
+  *x = tx * 8 + (w & 7);
+  *y = ty * 4 + (w >> 3);
+  *sample = J.first_sample + (int)k;
+  return *x < J.cam.W && *y < J.cam.H;
+}
+
+#define VSLOT(J, kind, j, i) ((size_t)((kind) * ((J).m + 1) + ((j)-1)) * (size_t)(J).B + (size_t)(i))
+
+__device__ inline float sqr(float x) { return x * x; }
+__device__ inline float clampS(float s) { return fminf(s, 1e30f); }
+
+// ---------------------------------------------------------------------------------------- walk
+__global__ void __launch_bounds__(128) k_walk(const Job J) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * J.B) return;
+  const int kind = i >= J.B ? 1 : 0;  // 0 eye, 1 light (warp-uniform: B is a multiple of 32)
+  const int si = i - kind * J.B;
+  int x, y, sample;
+  if (!decode_sample(J, J.g0 + (unsigned long long)si, &x, &y, &sample)) { J.counts[i] = 0; return; }
+  const DScene& sc = J.sc;
+  Rng rng;
+  rng.begin(J.seed, (unsigned long long)y * (unsigned long long)J.cam.W + (unsigned long long)x,
+            (unsigned long long)sample, (uint32_t)kind);
+
+  f3 o, d, prev_n, alpha, prev_f = mk3(1.f);
+  float tmin, tmax, prev_pdf, pdfeval_prev, D_prev, S_prev;
+  bool delta_prev = false;
+  int nv = 1;
+  if (kind == 0) {
+    // raytrace_pixel bidirection.cpp:517-524 and v1 of the eye subpath (:29-37)
+    float sx = rng.uniform(), sy = rng.uniform();
+    camera_generate_ray(J.cam, ((float)x + sx) / (float)J.cam.W, ((float)y + sy) / (float)J.cam.H, &o, &d);
+    tmin = J.cam.nclip; tmax = J.cam.fclip;
+    prev_n = d; alpha = mk3(1.f); prev_pdf = 1.f;
+    pdfeval_prev = 1.f; D_prev = 1.f; S_prev = 0.f;
+  } else {
+    // sample_light_ray bidirection.cpp:105-118 and v1 of the light subpath
+    int li = rng.pick(sc.n_lights);
+    Light L = load_light(sc, li);
+    float pA, pdir; f3 nl;
+    f3 Le = light_sample_Le(L, rng, &o, &d, &pA, &pdir, &nl);
+    pA /= (float)sc.n_lights;
+    tmin = BDPT_EPS_F; tmax = INFINITY;
+    prev_n = nl; alpha = Le * (1.0f / pA); prev_pdf = pdir;
+    pdfeval_prev = pdir; D_prev = pA; S_prev = 1.f;
+    size_t s1 = VSLOT(J, 1, 1, si);
+    J.v0[s1] = make_float4(o.x, o.y, o.z, __int_as_float(-1));
+    J.v1[s1] = make_float4(nl.x, nl.y, nl.z, pA);
+    J.v2[s1] = make_float4(alpha.x, alpha.y, alpha.z, 1.f);
+    J.v3[s1] = make_float4(pdir, 0.f, 0.f, 1.f);
+  }
+
+  unsigned int nrays = 0;
+  for (int j = 2; j <= J.m + 1; j++) {
+    Hit h = traverse<false>(sc, o, d, tmin, tmax);
+    nrays++;
+    if (h.leaf < 0) break;
+    f3 n; int prim, mat;
+    finish_hit(sc, h, o, d, &n, &prim, &mat);
+    const f3 hit_p = o + d * h.t;
+    const Frame fr = make_frame(n);
+    const f3 w_out = fr.to_local(-d);
+    const Mat M = load_mat(sc, mat);
+    f3 wi; float pdf;
+    const f3 f = bsdf_sample_f(M, w_out, &wi, &pdf, rng);
+    const f3 wi_world = normalized(fr.to_world(wi));
+
+    // bidirection.cpp:64-69
+    const float cos_prev = fabsf(dot(prev_n, d));
+    const float g = cos_prev * fabsf(dot(n, d)) / (h.t * h.t);
+    alpha = alpha * prev_f * (cos_prev / prev_pdf);
+
+    // roulette (off in the reference: bidirection.cpp:80; the disabled rule is :87-93)
+    float p_keep = 1.f;
+    if (J.roulette && j > 2) p_keep = fminf(1.f, norm(f) / pdf);
+
+    // MIS cache
+    const bool delta_j = type_is_delta(M.type);
+    const float D_j = (kind == 0 && j == 2) ? 1.f : pdfeval_prev * g;
+    const f3 zero = mk3(0.f);
+    const float D_rev = bsdf_pdf(M, zero, w_out) * p_keep * g;  // density of (j -> j-1) as the chains use it
+    float S_j = (delta_j || delta_prev) ? 0.f : 1.f;
+    if (S_prev > 0.f) { float R = D_rev / D_prev; S_j += R * R * S_prev; }
+    S_j = clampS(S_j);
+
+    size_t sl = VSLOT(J, kind, j, si);
+    J.v0[sl] = make_float4(hit_p.x, hit_p.y, hit_p.z, __int_as_float(mat));
+    J.v1[sl] = make_float4(n.x, n.y, n.z, D_j);
+    J.v2[sl] = make_float4(alpha.x, alpha.y, alpha.z, S_j);
+    J.v3[sl] = make_float4(-d.x, -d.y, -d.z, p_keep);
+    nv = j;
+    if (j >= J.m + 1) break;
+    if (J.roulette && !(rng.uniform() < p_keep)) break;
+    if (is_zero(f)) break;  // throughput is exactly zero from here on: later vertices add nothing
+
+    pdfeval_prev = bsdf_pdf(M, zero, wi) * p_keep;
+    prev_f = f; prev_n = n; prev_pdf = pdf * p_keep;
+    D_prev = D_j; S_prev = S_j; delta_prev = delta_j;
+    o = hit_p; d = wi_world; tmin = BDPT_EPS_F; tmax = INFINITY;
+  }
+  J.counts[i] = nv;
+  // one atomic per warp for the ray counter
+  unsigned int tot = __reduce_add_sync(__activemask(), nrays);
+  if ((threadIdx.x & 31) == (__ffs(__activemask()) - 1)) atomicAdd(J.stats + 0, (unsigned long long)tot);
+}
+
+// ------------------------------------------------------------------------------------- connect
+struct Vtx {
+  f3 pos, n, alpha, wo;
+  float D, S, q;
+  int mat;
+};
+
+__device__ inline Vtx load_vtx(const Job& J, int kind, int j, int si) {
+  size_t s = VSLOT(J, kind, j, si);
+  float4 a = J.v0[s], b = J.v1[s], c = J.v2[s], e = J.v3[s];
+  Vtx v;
+  v.pos = mk3(a.x, a.y, a.z); v.mat = __float_as_int(a.w);
+  v.n = mk3(b.x, b.y, b.z); v.D = b.w;
+  v.alpha = mk3(c.x, c.y, c.z); v.S = c.w;
+  v.wo = mk3(e.x, e.y, e.z); v.q = e.w;
+  return v;
+}
+
+__device__ inline void push_shadow(const Job& J, bool push, f3 o, f3 dir, float tmax, unsigned int target, f3 ill) {
+  const unsigned int active = __activemask();
+  const unsigned int mask = __ballot_sync(active, push);
+  if (mask == 0u) return;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(mask) - 1;
+  unsigned int base = 0;
+  if (lane == leader) base = atomicAdd(J.qctr + 0, (unsigned int)__popc(mask));
+  base = __shfl_sync(active, base, leader);
+  if (!push) return;
+  unsigned int idx = base + __popc(mask & ((1u << lane) - 1u));
+  if (idx >= J.qcap) { J.qctr[2] = 1u; return; }
+  J.q0[idx] = make_float4(o.x, o.y, o.z, tmax);
+  J.q1[idx] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(target));
+  J.q2[idx] = make_float4(ill.x, ill.y, ill.z, 0.f);
+}
+
+template <bool TRACE>
+__global__ void __launch_bounds__(128) k_connect(const Job J) {
+  const int si = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.y + 1;
+  if (si >= J.B) return;
+  const int nE = J.counts[si];
+  const int nL = J.counts[J.B + si];
+  if (nE == 0 || t > nE) return;  // invalid lane or the eye subpath is shorter than t
+  int x, y, sample;
+  decode_sample(J, J.g0 + (unsigned long long)si, &x, &y, &sample);
+  const DScene& sc = J.sc;
+  const f3 zero = mk3(0.f);
+
+  Vtx E; Mat ME; Frame frE;
+  E.mat = -1; E.D = 1.f; E.S = 0.f; E.q = 1.f;
+  if (t >= 2) {
+    E = load_vtx(J, 0, t, si);
+    ME = load_mat(sc, E.mat);
+    frE = make_frame(E.n);
+  } else {
+    E.pos = J.cam.pos; E.alpha = mk3(1.f); E.n = zero; E.wo = zero;
+    ME.type = -1;
+  }
+  const f3 woE = t >= 2 ? frE.to_local(E.wo) : zero;
+  const unsigned int pix_own = (unsigned int)(y * J.cam.W + x);
+  unsigned int nconn = 0;
+
+  for (int s = 0; s <= nL; s++) {
+    if (J.only_t >= 0 && (t != J.only_t || s != J.only_s)) continue;
+    f3 contrib = zero, ill = zero;
+    float w = 0.f;
+    int eye_x = -1, eye_y = -1;
+    nconn++;
+    if (s == 0) {
+      // c_{0,t}: the eye subpath hit an emitter (bidirection.cpp:307-328)
+      f3 c = (t >= 2 && ME.type == BDPT_MAT_EMISSION) ? ME.radiance : zero;
+      int lj = -1; Light L;
+      if (norm(c) > BDPT_EPS_F) {
+        for (int j = 0; j < sc.n_lights; j++) {
+          L = load_light(sc, j);
+          if (light_contain_point(L, E.pos)) { lj = j; break; }
+        }
+        if (lj < 0) c = zero;
+        else { float pp, dp; c = light_sample_pdf(L, E.pos, -E.wo, &pp, &dp); }
+      }
+      contrib = E.alpha * c;
+      if (norm(contrib) > BDPT_EPS_F && lj >= 0) {
+        // MIS, eye chain only (bidirection.cpp:159-176,181-188)
+        const float r_t = (1.0f / L.area) / E.D;
+        float tail = 0.f;
+        bool delta_prev = false;
+        if (t >= 3) {
+          Vtx P = load_vtx(J, 0, t - 1, si);
+          delta_prev = type_is_delta(mat_type(sc, P.mat));
+          if (P.S > 0.f) {
+            float pp, dp;
+            light_sample_pdf(L, E.pos, -E.wo, &pp, &dp);  // dir pdf of leaving the light toward e_{t-1}
+            f3 wv = P.pos - E.pos; float d2 = dot(wv, wv);
+            f3 wd = wv * rsqrtf(d2);
+            float gp = fabsf(dot(frE.z, wd) * dot(wd, P.n)) / d2;
+            float Rp = dp * gp / P.D;
+            tail = Rp * Rp * P.S;
+          }
+        }
+        double winv = 1.0 + (double)r_t * (double)r_t * ((double)(delta_prev ? 0.f : 1.f) + (double)tail);
+        w = (float)(1.0 / winv);
+        if (!(w >= 0.f)) w = 0.f;
+        ill = contrib * w;
+        float* px = J.acc_eye + 3 * (size_t)pix_own;
+        atomicAdd(px + 0, ill.x); atomicAdd(px + 1, ill.y); atomicAdd(px + 2, ill.z);
+      }
+    } else {
+      // ---- light-side endpoint vl
+      Vtx Lv; Mat ML; Frame frL;
+      float ls_dir_pdf = 0.f;
+      if (s == 1) {
+        // fresh light point for this t (bidirection.cpp:332-358)
+        Rng rng;
+        rng.begin(J.seed, (unsigned long long)pix_own, (unsigned long long)sample, 2u + (uint32_t)t);
+        int li = rng.pick(sc.n_lights);
+        Light L = load_light(sc, li);
+        float pA;
+        f3 rad = light_sample_Le_point(L, E.pos, rng, &Lv.pos, &pA, &ls_dir_pdf, &Lv.n);
+        pA /= (float)sc.n_lights;
+        Lv.alpha = rad * (1.0f / pA);
+        Lv.mat = -1; Lv.q = 1.f; Lv.D = pA; Lv.S = 1.f; Lv.wo = zero;
+        ML.type = -1;
+      } else {
+        Lv = load_vtx(J, 1, s, si);
+        ML = load_mat(sc, Lv.mat);
+      }
+      if (s >= 2) frL = make_frame(Lv.n);
+      // ---- eye-side endpoint ve (t == 1: the pinhole, bidirection.cpp:360-383)
+      f3 ve_pos = E.pos, ve_n = E.n, eye_alpha = E.alpha;
+      float cam_dir_pdf = 0.f;
+      if (t == 1) {
+        f3 wi; float dist;
+        float We = camera_sample_ray_pdf(J.cam, Lv.pos, &wi, &dist, &cam_dir_pdf, &eye_x, &eye_y);
+        ve_n = -wi;
+        eye_alpha = mk3(We);
+      }
+      f3 cv = Lv.pos - ve_pos;
+      const float dist2 = dot(cv, cv);
+      const float dist = sqrtf(dist2);
+      const f3 cdir = cv * (1.0f / dist);
+      // bsdf->f at both ends (bidirection.cpp:385-416)
+      f3 f_eye = mk3(1.f), f_light = mk3(1.f);
+      f3 cE = zero, cL = zero;
+      if (t >= 2) { cE = frE.to_local(cdir); f_eye = bsdf_f(ME, woE, cE); }
+      if (s >= 2) { cL = frL.to_local(-cdir); f_light = bsdf_f(ML, cL, frL.to_local(Lv.wo)); }
+      const float g = fabsf(dot(Lv.n, cdir) * dot(ve_n, cdir)) / dist2;
+      contrib = eye_alpha * Lv.alpha * (f_eye * f_light) * g;
+      bool push = false;
+      unsigned int target = pix_own;
+      if (norm(contrib) > BDPT_EPS_F) {
+        // ---- MIS weight (bidirection.cpp:121-293 in closed form, see header)
+        double winv = 1.0;
+        if (t >= 2) {
+          float P_le = s == 1 ? ls_dir_pdf : bsdf_pdf(ML, zero, cL) * Lv.q;
+          float r_t = P_le * g / E.D;
+          winv += (double)r_t * (double)r_t * (double)E.S;
+        }
+        if (s >= 2) {
+          float P_el = t == 1 ? cam_dir_pdf : bsdf_pdf(ME, zero, cE) * E.q;
+          float r_s = P_el * g / Lv.D;
+          winv += (double)r_s * (double)r_s * (double)Lv.S;
+        } else {
+          // s == 1: the chain is evaluated at the ORIGINAL light-subpath origin
+          size_t s1 = VSLOT(J, 1, 1, si);
+          float4 a = J.v0[s1], b = J.v1[s1];
+          f3 wv = mk3(a.x, a.y, a.z) - ve_pos;
+          float d2 = dot(wv, wv);
+          f3 wd = wv * rsqrtf(d2);
+          float cosA, P_el;
+          if (t == 1) { cosA = dot(ve_n, wd); P_el = cam_dir_pdf; }
+          else { f3 wl = frE.to_local(wd); cosA = wl.z; P_el = bsdf_pdf(ME, zero, wl) * E.q; }
+          float gp = fabsf(cosA * dot(wd, mk3(b.x, b.y, b.z))) / d2;
+          float r_s = P_el * gp / b.w;
+          winv += (double)r_s * (double)r_s;
+        }
+        w = (float)(1.0 / winv);
+        if (!(w >= 0.f)) w = 0.f;  // NaN guard
+        ill = contrib * w;
+        push = w > 0.f;
+        if (t == 1) {
+          if (eye_x >= 0 && eye_y >= 0 && eye_x < J.cam.W && eye_y < J.cam.H)
+            target = (unsigned int)(eye_y * J.cam.W + eye_x) | 0x80000000u;
+          else push = false;
+        }
+      }
+      if (TRACE) {
+        // trace mode resolves visibility inline so that the record says "occluded" (NaN) like the oracle's
+        Hit h = traverse<true>(sc, ve_pos, cdir, BDPT_EPS_F, dist - BDPT_EPS_F);
+        if (h.leaf >= 0) { contrib = mk3(NAN); w = NAN; push = false; eye_x = eye_y = -1; }
+      }
+      push_shadow(J, push, ve_pos, cdir, dist - BDPT_EPS_F, target, ill);
+    }
+    if (TRACE && J.dbg) {
+      double* r = J.dbg + 8 * ((size_t)(t - 1) * (size_t)(J.m + 2) + (size_t)s);
+      r[0] = t; r[1] = s; r[2] = contrib.x; r[3] = contrib.y; r[4] = contrib.z; r[5] = w; r[6] = eye_x; r[7] = eye_y;
+    }
+  }
+  unsigned int tot = __reduce_add_sync(__activemask(), nconn);
+  if ((threadIdx.x & 31) == (__ffs(__activemask()) - 1)) atomicAdd(J.stats + 2, (unsigned long long)tot);
+}
+
+// -------------------------------------------------------------------------------------- shadow
+// Persistent warps: each warp claims 32 queue entries with one atomic, traces them any-hit and
+// splats the survivors.  Grid = (resident CTAs per SM) x 148.
+__global__ void __launch_bounds__(128) k_shadow(const Job J) {
+  const unsigned int n = min(J.qctr[0], J.qcap);
+  const int lane = threadIdx.x & 31;
+  unsigned int traced = 0;
+  for (;;) {
+    unsigned int base = 0;
+    if (lane == 0) base = atomicAdd(J.qctr + 1, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n) break;
+    unsigned int idx = base + lane;
+    if (idx < n) {
+      float4 a = J.q0[idx], b = J.q1[idx];
+      Hit h = traverse<true>(J.sc, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), BDPT_EPS_F, a.w);
+      traced++;
+      if (h.leaf < 0) {
+        float4 c = J.q2[idx];
+        unsigned int tg = __float_as_uint(b.w);
+        float* px = ((tg & 0x80000000u) ? J.acc_light : J.acc_eye) + 3 * (size_t)(tg & 0x7fffffffu);
+        atomicAdd(px + 0, c.x); atomicAdd(px + 1, c.y); atomicAdd(px + 2, c.z);
+      }
+    }
+  }
+  unsigned int tot = __reduce_add_sync(0xffffffffu, traced);
+  if (lane == 0 && tot) atomicAdd(J.stats + 1, (unsigned long long)tot);
+}
+
+// ------------------------------------------------------------------------------ test-hook kernels
+__global__ void k_intersect_batch(DScene sc, const float* rays, size_t n, float* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* r = rays + 8 * i;
+  f3 o = mk3(r[0], r[1], r[2]), d = mk3(r[3], r[4], r[5]);
+  Hit h = traverse<false>(sc, o, d, r[6], r[7]);
+  float* q = out + 6 * i;
+  if (h.leaf < 0) { q[0] = -1.f; q[1] = INFINITY; q[2] = q[3] = q[4] = 0.f; q[5] = -1.f; return; }
+  f3 nn; int prim, mat;
+  finish_hit(sc, h, o, d, &nn, &prim, &mat);
+  q[0] = __int_as_float(prim); q[1] = h.t; q[2] = nn.x; q[3] = nn.y; q[4] = nn.z; q[5] = __int_as_float(mat);
+}
+
+__global__ void k_occluded_batch(DScene sc, const float* rays, size_t n, int* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* r = rays + 8 * i;
+  Hit h = traverse<true>(sc, mk3(r[0], r[1], r[2]), mk3(r[3], r[4], r[5]), r[6], r[7]);
+  out[i] = h.leaf >= 0 ? 1 : 0;
+}
+
+__global__ void k_bsdf_eval(DScene sc, const float* in, size_t n, float* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* q = in + 7 * i; float* o = out + 8 * i;
+  Mat M = load_mat(sc, (int)q[0]);
+  f3 wo = mk3(q[1], q[2], q[3]), wi = mk3(q[4], q[5], q[6]);
+  f3 f = bsdf_f(M, wo, wi);
+  o[0] = f.x; o[1] = f.y; o[2] = f.z;
+  o[3] = M.type == BDPT_MAT_MICROFACET ? NAN : bsdf_pdf(M, mk3(0.f), wi);
+  o[4] = type_is_delta(M.type) ? 1.f : 0.f;
+  f3 e = M.type == BDPT_MAT_EMISSION ? M.radiance : mk3(0.f);
+  o[5] = e.x; o[6] = e.y; o[7] = e.z;
+}
+
+// explicit-uniform sampler: a tiny Rng stand-in that replays q[4..6] = {u1, u2, u_coin}
+struct ScriptRng {
+  const float* u; int pos;
+  __device__ float uniform() { return u[pos++]; }
+};
+
+__global__ void k_bsdf_sample(DScene sc, const float* in, size_t n, float* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* q = in + 7 * i; float* o = out + 7 * i;
+  Mat M = load_mat(sc, (int)q[0]);
+  ScriptRng rng; rng.u = q + 4; rng.pos = M.type == BDPT_MAT_GLASS ? 2 : 0;  // glass draws only the coin
+  f3 wi; float pdf = 0.f;
+  f3 f = bsdf_sample_f(M, mk3(q[1], q[2], q[3]), &wi, &pdf, rng);
+  o[0] = wi.x; o[1] = wi.y; o[2] = wi.z; o[3] = pdf; o[4] = f.x; o[5] = f.y; o[6] = f.z;
+}
+
+__global__ void k_light_eval(DScene sc, const float* in, size_t n, float* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* q = in + 7 * i; float* o = out + 6 * i;
+  Light L = load_light(sc, (int)q[0]);
+  f3 p = mk3(q[1], q[2], q[3]), wi = mk3(q[4], q[5], q[6]);
+  float pp = 0.f, dp = 0.f;
+  o[0] = light_contain_point(L, p) ? 1.f : 0.f;
+  f3 le = light_sample_pdf(L, p, wi, &pp, &dp);
+  o[1] = le.x; o[2] = le.y; o[3] = le.z; o[4] = pp; o[5] = dp;
+}
+
+__global__ void k_camera_eval(DCamera cam, const float* in, size_t n, float* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* q = in + 5 * i; float* o = out + 11 * i;
+  f3 ro, rd;
+  camera_generate_ray(cam, q[0], q[1], &ro, &rd);
+  o[0] = ro.x; o[1] = ro.y; o[2] = ro.z; o[3] = rd.x; o[4] = rd.y; o[5] = rd.z;
+  f3 wi; float dist, dp; int px, py;
+  float We = camera_sample_ray_pdf(cam, mk3(q[2], q[3], q[4]), &wi, &dist, &dp, &px, &py);
+  o[6] = We; o[7] = dp; o[8] = (float)px; o[9] = (float)py; o[10] = dist;
+}
+
+// toColor, reference util/image.h:194-209: exposure sqrt(2), gamma 2.2, clamp, truncate to u8.
+// Output row 0 = top (RaytracedRenderer::save_image flips, raytraced_renderer.cpp:690-728).
+__global__ void k_tonemap(const float* eye, const float* light, int which, float inv_ns, int W, int H, uint8_t* rgba) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= W * H) return;
+  int x = p % W, y = p / W;
+  float v[3];
+  for (int c = 0; c < 3; c++) {
+    float e = eye[3 * p + c], l = light[3 * p + c];
+    v[c] = (which == 0 ? e + l : which == 1 ? e : l) * inv_ns;
+  }
+  uint8_t* o = rgba + 4 * ((size_t)(H - 1 - y) * W + x);
+  for (int c = 0; c < 3; c++) {
+    float g = powf(fmaxf(v[c], 0.f) * 1.41421356f, 1.0f / 2.2f);
+    g = fminf(fmaxf(g, 0.f), 1.f);
+    o[c] = (uint8_t)(g * 255.f);
+  }
+  o[3] = 255;
+}
+
+__global__ void k_resolve(const float* eye, const float* light, int which, float inv_ns, size_t n, float* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float e = eye[i], l = light[i];
+  out[i] = (which == 0 ? e + l : which == 1 ? e : l) * inv_ns;
+}
+
+}  // namespace bdpt

@@ -1,0 +1,336 @@
+// shading.cuh — BSDF, light and camera device functions (fp32).
+// Each function states the reference function whose behaviour it reproduces
+// (paths relative to the reference tree).  Local directions are in the frame of
+// make_frame() (z = shading normal).
+#pragma once
+#include "common.cuh"
+#include "rng.cuh"
+#include "../../include/bdpt_flatscene.h"
+
+namespace bdpt {
+
+struct Mat {
+  int type;
+  f3 reflectance, transmittance, radiance, eta, k;
+  float alpha, ior;
+};
+
+__device__ inline int mat_type(const DScene& sc, int m) { return __float_as_int(ldg4(sc.materials + 5 * m).w); }
+
+__device__ inline bool type_is_delta(int type) {  // BSDF::is_delta of each class, bsdf.h
+  return type == BDPT_MAT_MIRROR || type == BDPT_MAT_GLASS || type == BDPT_MAT_REFRACTION;
+}
+
+__device__ inline Mat load_mat(const DScene& sc, int m) {
+  Mat r;
+  const float4* p = sc.materials + 5 * m;
+  float4 a = ldg4(p), b = ldg4(p + 1), c = ldg4(p + 2);
+  r.reflectance = mk3(a.x, a.y, a.z); r.type = __float_as_int(a.w);
+  r.transmittance = mk3(b.x, b.y, b.z); r.ior = b.w;
+  r.radiance = mk3(c.x, c.y, c.z); r.alpha = c.w;
+  if (r.type == BDPT_MAT_MICROFACET) {
+    float4 d = ldg4(p + 3), e = ldg4(p + 4);
+    r.eta = mk3(d.x, d.y, d.z); r.k = mk3(e.x, e.y, e.z);
+  } else { r.eta = mk3(0.f); r.k = mk3(0.f); }
+  return r;
+}
+
+// sampler.cpp:91-94  CosineWeightedHemisphereSampler3D::pdf
+__device__ inline float cosine_pdf(float z) { return z > 0.f ? z * BDPT_INV_PI : 0.f; }
+
+// sampler.cpp:76-85  CosineWeightedHemisphereSampler3D::get_sample(pdf)
+__device__ inline f3 cosine_hemisphere(float xi1, float xi2, float* pdf) {
+  float r = sqrtf(xi1);
+  float s, c;
+  sincospif(2.0f * xi2, &s, &c);
+  float z = sqrtf(1.0f - xi1);
+  *pdf = z * BDPT_INV_PI;
+  return mk3(r * c, r * s, z);
+}
+
+// sampler.cpp:17-24  UniformSphereSampler3D::get_sample
+__device__ inline f3 uniform_sphere(float u1, float u2) {
+  float z = u1 * 2.f - 1.f;
+  float st = sqrtf(fmaxf(0.f, 1.f - z * z));
+  float s, c;
+  sincospif(2.0f * u2, &s, &c);
+  return mk3(c * st, s * st, z);
+}
+
+// advanced_bsdf.cpp:280-303  BSDF::refract
+__device__ inline bool refract_local(f3 wo, f3* wi, float ior) {
+  bool enter = wo.z > 0.f;
+  float eta = enter ? 1.0f / ior : ior;
+  float z_sq = 1.f - eta * eta * (1.f - wo.z * wo.z);
+  if (z_sq < 0.f) return false;
+  *wi = mk3(-eta * wo.x, -eta * wo.y, enter ? -sqrtf(z_sq) : sqrtf(z_sq));
+  return true;
+}
+
+__device__ inline float pow5(float x) { float x2 = x * x; return x2 * x2 * x; }
+
+// Schlick term of GlassBSDF (advanced_bsdf.cpp:214-222 and :247-253)
+__device__ inline float glass_R(float ior, f3 refr, bool wo_z_positive) {
+  float c = fabsf(refr.z) / norm(refr);
+  float eta = wo_z_positive ? 1.0f / ior : ior;
+  float r0 = (1.f - eta) / (1.f + eta);
+  r0 *= r0;
+  return r0 + (1.f - r0) * pow5(1.f - c);
+}
+
+// Microfacet helpers: bsdf.h:176-184 (getTheta, Lambda), advanced_bsdf.cpp:48-82 (G, D, F)
+__device__ inline float mf_lambda(float alpha, float wz) {
+  float cz = fminf(fmaxf(wz, -1.0f + 1e-5f), 1.0f - 1e-5f);
+  float tan_t = sqrtf(fmaxf(0.f, 1.f - cz * cz)) / cz;
+  float a = 1.0f / (alpha * tan_t);
+  return 0.5f * (erff(a) - 1.0f + expf(-a * a) / (a * BDPT_PI));
+}
+__device__ inline float mf_D(float alpha, float hz) {
+  float c2 = hz * hz;
+  float tan2 = (1.f - c2) / c2;
+  return expf(-tan2 / (alpha * alpha)) / (BDPT_PI * alpha * alpha * c2 * c2);
+}
+__device__ inline f3 mf_F(const Mat& m, f3 wi) {
+  float c = fabsf(wi.z) / norm(wi);
+  float c2 = c * c;
+  f3 e2k2 = m.eta * m.eta + m.k * m.k;
+  f3 tec = 2.f * c * m.eta;
+  f3 rs, rp;
+  rs.x = (e2k2.x - tec.x + c2) / (e2k2.x + tec.x + c2);
+  rs.y = (e2k2.y - tec.y + c2) / (e2k2.y + tec.y + c2);
+  rs.z = (e2k2.z - tec.z + c2) / (e2k2.z + tec.z + c2);
+  rp.x = (e2k2.x * c2 - tec.x + 1.f) / (e2k2.x * c2 + tec.x + 1.f);
+  rp.y = (e2k2.y * c2 - tec.y + 1.f) / (e2k2.y * c2 + tec.y + 1.f);
+  rp.z = (e2k2.z * c2 - tec.z + 1.f) / (e2k2.z * c2 + tec.z + 1.f);
+  return (rs + rp) * 0.5f;
+}
+
+// BSDF::f(wo, wi): bsdf.cpp:52-60 diffuse; :99-101 emission; advanced_bsdf.cpp:17-19,
+// :159-161,:194-196 mirror/refraction/glass (all zero); :84-95 microfacet.
+__device__ inline f3 bsdf_f(const Mat& m, f3 wo, f3 wi) {
+  if (m.type == BDPT_MAT_DIFFUSE) {
+    if (wo.z < 0.f || wi.z < 0.f) return mk3(0.f);
+    return m.reflectance * BDPT_INV_PI;
+  }
+  if (m.type == BDPT_MAT_MICROFACET) {
+    if (wo.z <= BDPT_EPS_F || wi.z <= BDPT_EPS_F) return mk3(0.f);
+    f3 h = normalized(wo + wi);
+    float G = 1.0f / (1.0f + mf_lambda(m.alpha, wi.z) + mf_lambda(m.alpha, wo.z));
+    return mf_F(m, wi) * (G * mf_D(m.alpha, h.z) / (4.f * wo.z * wi.z));
+  }
+  return mk3(0.f);
+}
+
+// BSDF::sample_pdf(wo, wi): bsdf.cpp:76-81,112-117; advanced_bsdf.cpp:31-34,180-183,236-259.
+// The reference's MIS always passes wo = (0,0,0) (bidirection.cpp:150,241): callers here pass
+// wo_z = 0 for that.  Microfacet: the reference aborts (advanced_bsdf.cpp:144-148); here it
+// returns the half-vector density sample_f uses (needs the real wo).
+__device__ inline float bsdf_pdf(const Mat& m, f3 wo, f3 wi) {
+  switch (m.type) {
+    case BDPT_MAT_DIFFUSE:
+    case BDPT_MAT_EMISSION:
+      return cosine_pdf(wi.z);
+    case BDPT_MAT_MIRROR:
+    case BDPT_MAT_REFRACTION:
+      return 1.f;
+    case BDPT_MAT_GLASS: {
+      f3 refr;
+      if (!refract_local(wi, &refr, m.ior)) return 1.f;
+      float R = glass_R(m.ior, refr, wo.z > 0.f);
+      return wi.z > 0.f ? R : 1.f - R;
+    }
+    case BDPT_MAT_MICROFACET: {
+      if (wo.z <= BDPT_EPS_F || wi.z <= BDPT_EPS_F) return 0.f;
+      f3 h = normalized(wo + wi);
+      float c2 = h.z * h.z;
+      float tan2 = (1.f - c2) / c2;
+      // p_theta * p_phi / sin(theta) of advanced_bsdf.cpp:126-130
+      float pdf_h = 2.f * expf(-tan2 / (m.alpha * m.alpha)) / (m.alpha * m.alpha * c2 * h.z) * (0.5f * BDPT_INV_PI);
+      return pdf_h / (4.f * dot(wi, h));
+    }
+  }
+  return 0.f;
+}
+
+// BSDF::sample_f(wo, &wi, &pdf): bsdf.cpp:65-74 diffuse; :106-110 emission;
+// advanced_bsdf.cpp:21-29 mirror; :163-175 refraction; :198-234 glass; :97-141 microfacet.
+// Draw order follows the reference: two uniforms for a hemisphere sample (Xi1 then Xi2), one coin
+// for glass only when refraction is possible.
+template <class RNG>
+__device__ inline f3 bsdf_sample_f(const Mat& m, f3 wo, f3* wi, float* pdf, RNG& rng) {
+  switch (m.type) {
+    case BDPT_MAT_DIFFUSE: {
+      float u1 = rng.uniform(), u2 = rng.uniform();
+      *wi = cosine_hemisphere(u1, u2, pdf);
+      return bsdf_f(m, wo, *wi);
+    }
+    case BDPT_MAT_EMISSION: {
+      float u1 = rng.uniform(), u2 = rng.uniform();
+      *wi = cosine_hemisphere(u1, u2, pdf);
+      return mk3(0.f);
+    }
+    case BDPT_MAT_MIRROR: {
+      *wi = mk3(-wo.x, -wo.y, wo.z);
+      *pdf = 1.f;
+      float c = fabsf(wi->z) / norm(*wi);
+      return m.reflectance * (1.0f / c);
+    }
+    case BDPT_MAT_REFRACTION: {
+      if (!refract_local(wo, wi, m.ior)) {  // reference leaves wi/pdf undefined on TIR; zero throughput either way
+        *wi = mk3(-wo.x, -wo.y, wo.z); *pdf = 1.f;
+        return mk3(0.f);
+      }
+      *pdf = 1.f;
+      float eta = wo.z > 0.f ? 1.0f / m.ior : m.ior;
+      float c = fabsf(wi->z) / norm(*wi);
+      return m.transmittance * (1.0f / (c * eta * eta));
+    }
+    case BDPT_MAT_GLASS: {
+      f3 wr = mk3(-wo.x, -wo.y, wo.z), wt;
+      if (!refract_local(wo, &wt, m.ior)) {
+        *pdf = 1.f; *wi = wr;
+        float c = fabsf(wr.z) / norm(wo);
+        return m.reflectance * (1.0f / c);
+      }
+      float eta = wo.z > 0.f ? 1.0f / m.ior : m.ior;
+      float R = glass_R(m.ior, wt, wo.z > 0.f);
+      if (rng.uniform() < R) {
+        *wi = wr; *pdf = R;
+        float c = fabsf(wr.z) / norm(wr);
+        return m.reflectance * (R / c);
+      } else {
+        *wi = wt; *pdf = 1.f - R;
+        float c = fabsf(wt.z) / norm(wt);
+        return m.transmittance * ((1.f - R) / (c * eta * eta));
+      }
+    }
+    case BDPT_MAT_MICROFACET: {
+      float rx = rng.uniform(), ry = rng.uniform();
+      float tan2 = -m.alpha * m.alpha * logf(1.f - rx);
+      float ct = rsqrtf(1.f + tan2), st = sqrtf(tan2) * ct;
+      float s, c;
+      sincospif(2.f * ry, &s, &c);
+      f3 h = mk3(st * c, st * s, ct);
+      float nwo = norm(wo);
+      float cth = dot(wo, h) / nwo;
+      f3 hp = h * (cth * nwo);
+      *wi = normalized(hp - (wo - hp));
+      if (wo.z <= BDPT_EPS_F || wi->z <= BDPT_EPS_F) { *pdf = 1.f; *wi = mk3(0.f, 0.f, 1.f); return mk3(0.f); }
+      float pdf_h = 2.f * expf(-tan2 / (m.alpha * m.alpha)) / (m.alpha * m.alpha * ct * ct * ct) * (0.5f * BDPT_INV_PI);
+      *pdf = pdf_h / (4.f * dot(*wi, h));
+      return bsdf_f(m, wo, *wi);
+    }
+  }
+  *pdf = 1.f; *wi = mk3(0.f, 0.f, 1.f);
+  return mk3(0.f);
+}
+
+// ------------------------------------------------------------------ lights
+struct Light {
+  int type;
+  f3 radiance, position, direction, dim_x, dim_y;
+  float area;
+};
+
+__device__ inline Light load_light(const DScene& sc, int i) {
+  const float4* p = sc.lights + 5 * i;
+  float4 a = ldg4(p), b = ldg4(p + 1), c = ldg4(p + 2), d = ldg4(p + 3), e = ldg4(p + 4);
+  Light l;
+  l.radiance = mk3(a.x, a.y, a.z); l.type = __float_as_int(a.w);
+  l.position = mk3(b.x, b.y, b.z); l.area = b.w;
+  l.direction = mk3(c.x, c.y, c.z);
+  l.dim_x = mk3(d.x, d.y, d.z); l.dim_y = mk3(e.x, e.y, e.z);
+  return l;
+}
+
+// AreaLight::contain_point light.cpp:257-262 (a plane test only); PointLight :136-139
+__device__ inline bool light_contain_point(const Light& l, f3 p) {
+  if (l.type == BDPT_LIGHT_AREA) {
+    f3 d = normalized(l.position - p);
+    return fabsf(dot(d, l.direction)) < BDPT_EPS_F;
+  }
+  return norm(p - l.position) < BDPT_EPS_F;
+}
+
+// AreaLight::sample_pdf light.cpp:264-284; PointLight::sample_pdf :141-151.
+// wi points TOWARD the light (world space).  Returns Le.
+__device__ inline f3 light_sample_pdf(const Light& l, f3 p, f3 wi, float* point_pdf, float* dir_pdf) {
+  if (!light_contain_point(l, p)) { *point_pdf = 0.f; *dir_pdf = 0.f; return mk3(0.f); }
+  if (l.type == BDPT_LIGHT_POINT) { *point_pdf = 1.f; *dir_pdf = 0.25f * BDPT_INV_PI; return l.radiance; }
+  *point_pdf = 1.0f / l.area;
+  // local z of normalize(w2o * (-wi)); w2o's z row is the unit light direction
+  f3 zdir = normalized(l.direction);
+  float z = dot(zdir, -wi) / norm(wi);
+  *dir_pdf = cosine_pdf(z);
+  return *dir_pdf > 0.f ? l.radiance : mk3(0.f);
+}
+
+// AreaLight::sample_Le light.cpp:219-232; PointLight::sample_Le :115-123
+__device__ inline f3 light_sample_Le(const Light& l, Rng& rng, f3* o, f3* d, float* point_pdf, float* dir_pdf, f3* normal) {
+  if (l.type == BDPT_LIGHT_POINT) {
+    float u1 = rng.uniform(), u2 = rng.uniform();
+    *o = l.position; *d = uniform_sphere(u1, u2);
+    *point_pdf = 1.f; *dir_pdf = 0.25f * BDPT_INV_PI; *normal = *d;
+    return l.radiance;
+  }
+  float sx = rng.uniform() - 0.5f, sy = rng.uniform() - 0.5f;
+  *o = l.position + sx * l.dim_x + sy * l.dim_y;
+  float u1 = rng.uniform(), u2 = rng.uniform();
+  f3 dl = cosine_hemisphere(u1, u2, dir_pdf);
+  Frame fr = make_frame(l.direction);
+  *d = fr.to_world(dl);
+  *point_pdf = 1.0f / l.area;
+  *normal = l.direction;
+  return l.radiance;
+}
+
+// AreaLight::sample_Le_point light.cpp:234-255; PointLight::sample_Le_point :125-134
+__device__ inline f3 light_sample_Le_point(const Light& l, f3 p, Rng& rng, f3* point, float* point_pdf, float* dir_pdf,
+                                           f3* normal) {
+  if (l.type == BDPT_LIGHT_POINT) {
+    f3 wi = normalized(l.position - p);
+    *point = l.position; *point_pdf = 1.f; *dir_pdf = 0.25f * BDPT_INV_PI; *normal = -wi;
+    return l.radiance;
+  }
+  float sx = rng.uniform() - 0.5f, sy = rng.uniform() - 0.5f;
+  *point = l.position + sx * l.dim_x + sy * l.dim_y;
+  f3 d = *point - p;
+  float cos_theta = dot(d, l.direction);
+  f3 wi = d * (1.0f / norm(d));
+  *point_pdf = 1.0f / l.area;
+  *normal = l.direction;
+  *dir_pdf = cosine_pdf(dot(normalized(l.direction), -wi));
+  return cos_theta < 0.f ? l.radiance : mk3(0.f);
+}
+
+// ------------------------------------------------------------------ camera
+// Camera::generate_ray camera.cpp:191-212 (x, y in [0,1])
+__device__ inline void camera_generate_ray(const DCamera& c, float x, float y, f3* o, f3* d) {
+  f3 dir = mk3((2.f * x - 1.f) * c.tan_h, (2.f * y - 1.f) * c.tan_v, -1.f);
+  f3 w = dir.x * c.c2w_x + dir.y * c.c2w_y + dir.z * c.c2w_z;
+  *o = c.pos;
+  *d = normalized(w);
+}
+
+// Camera::sample_ray_pdf camera.cpp:214-248.  Returns We (a scalar; the reference returns it in all
+// three channels); wi points from p to the pinhole.
+__device__ inline float camera_sample_ray_pdf(const DCamera& c, f3 p, f3* wi, float* dist, float* dir_pdf, int* px, int* py) {
+  f3 v = c.pos - p;
+  *dist = norm(v);
+  *wi = v * (1.0f / *dist);
+  f3 mw = -(*wi);
+  f3 wc = mk3(dot(c.w2c_r0, mw), dot(c.w2c_r1, mw), -dot(c.w2c_r2, mw));
+  float cos_t = wc.z;  // cos(acos(wc.z))
+  float c2 = cos_t * cos_t;
+  float We = c2 * c2 / (4.f * c.tan_h * c.tan_v);
+  *dir_pdf = (*dist * *dist) / cos_t;
+  float inv = 1.0f / wc.z;
+  float fx = ((wc.x * inv / c.tan_h + 1.f) * 0.5f) * (float)c.W;
+  float fy = ((wc.y * inv / c.tan_v + 1.f) * 0.5f) * (float)c.H;
+  // C truncation toward zero, as the reference's double -> int conversion (camera.cpp:242-243)
+  *px = (fx > -2.0e9f && fx < 2.0e9f) ? __float2int_rz(fx) : -1;
+  *py = (fy > -2.0e9f && fy < 2.0e9f) ? __float2int_rz(fy) : -1;
+  return We;
+}
+
+}  // namespace bdpt

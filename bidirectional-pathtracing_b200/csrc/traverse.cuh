@@ -1,0 +1,167 @@
+// traverse.cuh — closest-hit / any-hit traversal of the compressed 8-wide BVH (bvh8.h).
+//
+// Replaces BVHAccel::intersect (reference src/scene/bvh.cpp:161-188, wrapper bvh.h:104-107),
+// BBox::intersect (src/scene/bbox.cpp:10-56), Triangle::intersect (src/scene/triangle.cpp:57-95)
+// and Sphere::intersect (src/scene/sphere.cpp:61-93).  Acceptance rules of the primitive tests are
+// the reference's: min_t <= t <= max_t inclusive, b1 >= 0, b2 >= 0, b1 + b2 <= 1, no backface or
+// determinant cull; a sphere reports its nearer root inside the interval, else the farther, and
+// only if t > 0.  The box test only culls, so the answer is the reference's closest hit (exact
+// ties between primitives excepted).
+//
+// Software traversal (B200 has no RT cores): a per-thread stack of "node group" entries
+// {child base index, hit bits | internal mask}; one entry per visited node regardless of how many
+// of its 8 children were hit, children popped nearest-first by count-leading-zeros on the hit bits,
+// which the builder's octant slot assignment makes a front-to-back order.
+#pragma once
+#include "common.cuh"
+
+namespace bdpt {
+
+#define BDPT_STACK 32
+
+struct Hit {
+  float t;
+  int leaf;  // index into the leaf-ordered primitive arrays, -1 = miss
+  float b1, b2;
+};
+
+// byte k of w as a float without an int->float conversion: PRMT builds 0x4B0000bb (= 2^23 + bb)
+__device__ inline float ubyte(uint32_t w, int k) {
+  return __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7650u + (uint32_t)k)) - 8388608.0f;
+}
+
+// Intersect one leaf primitive; returns true and shrinks tmax on an accepted hit.
+__device__ inline bool intersect_prim(const float4* __restrict__ prims, int k, f3 o, f3 d, float tmin, float& tmax,
+                                      float& b1o, float& b2o) {
+  float4 a = ldg4(prims + 3 * k), b = ldg4(prims + 3 * k + 1);
+  if (__float_as_int(b.w) >= 0) {  // triangle: a = {v0, prim id}, b = {e1, material}, c = {e2, -}
+    float4 c = ldg4(prims + 3 * k + 2);
+    f3 e1 = mk3(b.x, b.y, b.z), e2 = mk3(c.x, c.y, c.z);
+    f3 s = o - mk3(a.x, a.y, a.z);
+    f3 s1 = cross(d, e2), s2 = cross(s, e1);
+    float inv = 1.0f / dot(s1, e1);
+    float t = dot(s2, e2) * inv, b1 = dot(s1, s) * inv, b2 = dot(s2, d) * inv;
+    if (t >= tmin && t <= tmax && b1 >= 0.f && b2 >= 0.f && b1 + b2 <= 1.f) {
+      tmax = t; b1o = b1; b2o = b2;
+      return true;
+    }
+    return false;
+  }
+  // sphere: a = {centre, prim id}, b = {r, r^2, -, material | sign bit}
+  f3 oc = o - mk3(a.x, a.y, a.z);
+  float A = dot(d, d), hb = dot(oc, d);
+  f3 l = oc - d * (hb / A);
+  float disc = A * (b.y - dot(l, l));
+  if (disc < 0.f) return false;
+  float sd = sqrtf(disc), ia = 1.0f / A;
+  float t1 = (-hb - sd) * ia, t2 = (-hb + sd) * ia, t = -1.f;
+  if (t1 >= tmin && t1 <= tmax) t = t1;
+  else if (t2 >= tmin && t2 <= tmax) t = t2;
+  if (t > 0.f) { tmax = t; b1o = 0.f; b2o = 0.f; return true; }
+  return false;
+}
+
+template <bool ANY_HIT>
+__device__ inline Hit traverse(const DScene& sc, f3 o, f3 d, float tmin, float tmax) {
+  Hit hit;
+  hit.t = tmax; hit.leaf = -1; hit.b1 = 0.f; hit.b2 = 0.f;
+
+  const uint32_t oct = (d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u);
+  const uint32_t octinv = oct ^ 7u;
+  f3 idir;
+  idir.x = 1.0f / (fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x));
+  idir.y = 1.0f / (fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y));
+  idir.z = 1.0f / (fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z));
+
+  uint2 stack[BDPT_STACK];
+  int sp = 0;
+  uint2 group = make_uint2(0u, 0x80000000u);  // root: node 0, top priority bit
+
+  for (;;) {
+    // ---- pop the nearest internal child of the current group
+    uint32_t bit = 31u - (uint32_t)__clz(group.y);
+    group.y &= ~(1u << bit);
+    uint32_t base = group.x;
+    uint32_t imask_prev = group.y & 0xffu;
+    if (group.y > 0x00ffffffu) stack[sp++] = group;
+    uint32_t slot = (bit - 24u) ^ octinv;
+    uint32_t rel = __popc(imask_prev & ((1u << slot) - 1u));
+    const uint4* np = sc.nodes + (size_t)(base + rel) * 5;
+    uint4 q0 = ldg4(np), q1 = ldg4(np + 1), q2 = ldg4(np + 2), q3 = ldg4(np + 3), q4 = ldg4(np + 4);
+
+    f3 adj, org;
+    adj.x = __uint_as_float((q0.w & 0xffu) << 23) * idir.x;
+    adj.y = __uint_as_float(((q0.w >> 8) & 0xffu) << 23) * idir.y;
+    adj.z = __uint_as_float(((q0.w >> 16) & 0xffu) << 23) * idir.z;
+    org.x = (__uint_as_float(q0.x) - o.x) * idir.x;
+    org.y = (__uint_as_float(q0.y) - o.y) * idir.y;
+    org.z = (__uint_as_float(q0.z) - o.z) * idir.z;
+    const uint32_t imask = q0.w >> 24;
+
+    // near / far plane words per axis, chosen by the direction sign
+    uint32_t nx0 = (oct & 1u) ? q3.z : q2.x, nx1 = (oct & 1u) ? q3.w : q2.y;
+    uint32_t fx0 = (oct & 1u) ? q2.x : q3.z, fx1 = (oct & 1u) ? q2.y : q3.w;
+    uint32_t ny0 = (oct & 2u) ? q4.x : q2.z, ny1 = (oct & 2u) ? q4.y : q2.w;
+    uint32_t fy0 = (oct & 2u) ? q2.z : q4.x, fy1 = (oct & 2u) ? q2.w : q4.y;
+    uint32_t nz0 = (oct & 4u) ? q4.z : q3.x, nz1 = (oct & 4u) ? q4.w : q3.y;
+    uint32_t fz0 = (oct & 4u) ? q3.x : q4.z, fz1 = (oct & 4u) ? q3.y : q4.w;
+
+    uint32_t hitmask = 0u;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int k = i & 3;
+      uint32_t nxw = i < 4 ? nx0 : nx1, fxw = i < 4 ? fx0 : fx1;
+      uint32_t nyw = i < 4 ? ny0 : ny1, fyw = i < 4 ? fy0 : fy1;
+      uint32_t nzw = i < 4 ? nz0 : nz1, fzw = i < 4 ? fz0 : fz1;
+      uint32_t meta = ((i < 4 ? q1.z : q1.w) >> (8 * k)) & 0xffu;
+      float t0 = fmaxf(fmaxf(ubyte(nxw, k) * adj.x + org.x, ubyte(nyw, k) * adj.y + org.y),
+                       fmaxf(ubyte(nzw, k) * adj.z + org.z, tmin));
+      float t1 = fminf(fminf(ubyte(fxw, k) * adj.x + org.x, ubyte(fyw, k) * adj.y + org.y),
+                       fminf(ubyte(fzw, k) * adj.z + org.z, hit.t));
+      t1 *= 1.0000004f;  // keep the cull conservative under fp32 rounding
+      if (t0 <= t1) {
+        uint32_t inner = (meta & 0x18u) == 0x18u ? octinv : 0u;
+        hitmask |= (meta >> 5) << ((meta ^ inner) & 31u);
+      }
+    }
+    group = make_uint2(q1.x, (hitmask & 0xff000000u) | imask);
+
+    // ---- leaf primitives of this node that were hit
+    uint32_t tris = hitmask & 0x00ffffffu;
+    while (tris) {
+      int i = __ffs(tris) - 1;
+      tris &= tris - 1u;
+      int k = (int)q1.y + i;
+      if (intersect_prim(sc.prims, k, o, d, tmin, hit.t, hit.b1, hit.b2)) {
+        hit.leaf = k;
+        if (ANY_HIT) return hit;
+      }
+    }
+
+    if (group.y <= 0x00ffffffu) {
+      if (sp == 0) break;
+      group = stack[--sp];
+    }
+  }
+  return hit;
+}
+
+// Shading data of an accepted closest hit: interpolated (unflipped) unit normal, primitive id in
+// the reference's order and material id (Triangle::intersect triangle.cpp:80-87, Sphere :78-87).
+__device__ inline void finish_hit(const DScene& sc, const Hit& h, f3 o, f3 d, f3* n, int* prim_id, int* mat) {
+  float4 a = ldg4(sc.prims + 3 * h.leaf), b = ldg4(sc.prims + 3 * h.leaf + 1);
+  *prim_id = __float_as_int(a.w);
+  int mw = __float_as_int(b.w);
+  *mat = mw & 0x7fffffff;
+  if (mw >= 0) {
+    float4 n1 = ldg4(sc.shading + 3 * h.leaf), n2 = ldg4(sc.shading + 3 * h.leaf + 1), n3 = ldg4(sc.shading + 3 * h.leaf + 2);
+    float b0 = 1.f - h.b1 - h.b2;
+    f3 nn = mk3(n1.x, n1.y, n1.z) * b0 + h.b1 * mk3(n2.x, n2.y, n2.z) + h.b2 * mk3(n3.x, n3.y, n3.z);
+    *n = normalized(nn);
+  } else {
+    f3 p = o + h.t * d;
+    *n = normalized(p - mk3(a.x, a.y, a.z));
+  }
+}
+
+}  // namespace bdpt

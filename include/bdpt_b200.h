@@ -1,0 +1,135 @@
+/* bdpt_b200.h — C-ABI of the B200-native bidirectional path tracer (libbdpt_b200.so).
+ *
+ * This is the drop-in boundary for the reference's BDPT hot path.  The reference
+ * puts a per-pixel C++ virtual (`PathTracer::raytrace_pixel`, reference
+ * src/pathtracer/pathtracer.h:69, implemented by BidirectionalPathTracer,
+ * src/pathtracer/bidirection.cpp:503-542) behind `RaytracedRenderer`
+ * (src/pathtracer/raytraced_renderer.cpp).  A GPU wavefront cannot sit behind a
+ * per-pixel call, so the boundary is frame-granular: it replaces the role
+ * RaytracedRenderer plays behind `OfflineRenderer::{set_scene, set_camera,
+ * set_frame_size, render_to_file}` (src/application/renderer.h:14-99).
+ *
+ * Conventions: plain C, opaque handle, int status (0 = ok, <0 = error, message via
+ * bdpt_last_error), no C++ types or exceptions across the boundary, one host
+ * thread per handle.  Host pointers unless a name says `_device`.  Images are
+ * RGB float, W*H*3, ROW 0 = BOTTOM (reference util/image.h), linear radiance.
+ * There is no CPU fallback: every entry point that computes needs a CUDA device
+ * and fails with BDPT_ERR_CUDA without one.
+ */
+#ifndef BDPT_B200_H
+#define BDPT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "bdpt_flatscene.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct BdptContext BdptContext;
+
+enum BdptStatus {
+  BDPT_OK = 0,
+  BDPT_ERR_CUDA = -1,      /* CUDA runtime error (incl. no device) */
+  BDPT_ERR_ARG = -2,       /* bad argument / call order            */
+  BDPT_ERR_SCENE = -3,     /* scene rejected (unsupported light, bad indices, ...) */
+  BDPT_ERR_OVERFLOW = -4   /* internal queue overflow (a bug; never expected)      */
+};
+
+enum BdptBuffer {
+  BDPT_BUFFER_SUM = 0,   /* sampleBuffer  = eye + light  (bidirection.cpp:457-462,537-538) */
+  BDPT_BUFFER_EYE = 1,   /* eyeBuffer     (t >= 2 strategies, bidirection.h:81)            */
+  BDPT_BUFFER_LIGHT = 2  /* lightBuffer   (t == 1 splats)                                   */
+};
+
+enum BdptRenderFlags {
+  BDPT_FLAG_ROULETTE = 1  /* enable the rule the reference ships commented out (bidirection.cpp:87-93) */
+};
+
+typedef struct BdptRenderParams {
+  int32_t ns_total;      /* -s : samples per pixel of the whole frame (the 1/ns normalisation)   */
+  int32_t max_ray_depth; /* -m : PathTracer::max_ray_depth (pathtracer.h:74)                      */
+  int32_t first_sample;  /* this call renders sample indices [first_sample, first_sample+n_samples) */
+  int32_t n_samples;     /*   of every pixel — how a frame is sharded across GPUs                */
+  uint32_t flags;        /* BdptRenderFlags                                                       */
+  int32_t only_t;        /* test hook: >= 0 keeps only strategy (i_eye == only_t, i_light == only_s), */
+  int32_t only_s;        /*   the author's debug filter at bidirection.cpp:492-493; -1 = all        */
+  int32_t reserved;
+  uint64_t seed;         /* counter-based RNG key; streams are keyed (seed, pixel, sample index)   */
+} BdptRenderParams;
+
+typedef struct BdptStats {
+  uint64_t samples;          /* BDPT samples rendered since the last bdpt_clear                     */
+  uint64_t rays_closest;     /* closest-hit queries (subpath walks)                                 */
+  uint64_t rays_shadow;      /* shadow queries actually traced                                      */
+  uint64_t connections;      /* (s,t) strategies evaluated                                          */
+  uint64_t kernel_launches;  /* CUDA kernels launched by this library since bdpt_clear              */
+  double ms_total;           /* device time of the last bdpt_render (CUDA events on its stream)     */
+  double ms_walk;            /* ... of which: subpath walk kernel                                   */
+  double ms_connect;         /* ... connection + MIS kernel                                         */
+  double ms_shadow;          /* ... shadow-ray kernel                                               */
+  double ms_bvh_build;       /* host BVH build of the last upload                                   */
+  uint32_t bvh_nodes;        /* wide-BVH node count                                                 */
+  uint32_t batch_samples;    /* samples per wavefront batch of the last render                      */
+  uint32_t n_batches;        /* batches of the last render                                          */
+  uint32_t timed_batches;    /* ... of which the first timed_batches carry the per-kernel times above */
+} BdptStats;
+
+/* --- lifetime ----------------------------------------------------------------------------- */
+int bdpt_create(int device, BdptContext** out);
+void bdpt_destroy(BdptContext* ctx);
+/* Last error text of this handle (or of creation when ctx == NULL). Never NULL. */
+const char* bdpt_last_error(const BdptContext* ctx);
+/* Optional: run on a caller-owned CUDA stream (a cudaStream_t passed as void*), e.g. torch's. */
+int bdpt_set_stream(BdptContext* ctx, void* cuda_stream);
+
+/* --- scene / camera / frame : replaces RaytracedRenderer::set_scene (+build_accel),
+ *     set_camera, set_frame_size (raytraced_renderer.cpp:105-127,135-148,158-176,350-374) --- */
+int bdpt_upload_scene(BdptContext* ctx, const BdptCamera* camera, const BdptMaterial* materials, uint32_t n_materials,
+                      const BdptLight* lights, uint32_t n_lights, const BdptPrim* prims, uint32_t n_prims);
+int bdpt_set_camera(BdptContext* ctx, const BdptCamera* camera);
+/* Applies Camera::set_screen_size semantics (camera.cpp:83-89) and (re)allocates the frame buffers. */
+int bdpt_set_frame(BdptContext* ctx, int width, int height);
+
+/* --- render : replaces start_raytracing + the worker threads' raytrace_pixel loop
+ *     (raytraced_renderer.cpp:267-328,595-620; bidirection.cpp:503-542) -------------------- */
+int bdpt_clear(BdptContext* ctx);                               /* BidirectionalPathTracer::clear          */
+int bdpt_render(BdptContext* ctx, const BdptRenderParams* p);   /* accumulates; returns when the GPU is done */
+int bdpt_read_framebuffer(BdptContext* ctx, int which, float* rgb_out); /* D2H, already divided by ns_total  */
+/* Device pointer to the un-normalised fp32 accumulators (eye or light; W*H*3 floats) so that a
+ * multi-GPU caller can reduce them in place (ncclReduce / torch.distributed) before reading. */
+int bdpt_framebuffer_device(BdptContext* ctx, int which, void** device_ptr, size_t* n_floats);
+/* toColor (util/image.h:194-209): exposure sqrt(2), gamma 2.2, clamp, RGBA8, row 0 = TOP as PNGs want
+ * (RaytracedRenderer::save_image flips, raytraced_renderer.cpp:690-728). */
+int bdpt_tonemap_rgba8(BdptContext* ctx, int which, uint8_t* rgba_out);
+int bdpt_get_stats(BdptContext* ctx, BdptStats* out);
+
+/* --- test hooks (parity against the oracle) ------------------------------------------------ */
+/* rays: n x {o[3], d[3], tmin, tmax} fp64 -> hits: n x {prim id (-1 miss), t, n[3], material} fp64.
+ * Mirrors BVHAccel::intersect (bvh.h:104-107). */
+int bdpt_intersect_batch(BdptContext* ctx, const double* rays, size_t n, double* hits);
+/* Any-hit form used for shadow rays: occluded[i] = 1 if anything lies in [tmin, tmax]. */
+int bdpt_occluded_batch(BdptContext* ctx, const double* rays, size_t n, int32_t* occluded);
+/* in: n x {material, wo[3], wi[3]} -> out: n x {f[3], sample_pdf(0,wi), is_delta, emission[3]} (BSDF::f etc.) */
+int bdpt_bsdf_eval_batch(BdptContext* ctx, const double* in, size_t n, double* out);
+/* in: n x {material, wo[3], u1, u2, u_coin} -> out: n x {wi[3], pdf, f[3]} (BSDF::sample_f with explicit uniforms) */
+int bdpt_bsdf_sample_batch(BdptContext* ctx, const double* in, size_t n, double* out);
+/* in: n x {light, p[3], wi[3]} -> out: n x {contain_point, Le[3], point_pdf, dir_pdf} (SceneLight::sample_pdf) */
+int bdpt_light_eval_batch(BdptContext* ctx, const double* in, size_t n, double* out);
+/* in: n x {x, y, p[3]} -> out: n x {o[3], d[3], We, dir_pdf, raster x, raster y, dist}
+ * (Camera::generate_ray / sample_ray_pdf) */
+int bdpt_camera_eval_batch(BdptContext* ctx, const double* in, size_t n, double* out);
+/* One BDPT sample, fully recorded.  out (capacity cap doubles) receives
+ *   [n_eye, n_light, n_eye x 13 vertex records, n_light x 13 vertex records,
+ *    then per evaluated strategy {t, s, contrib[3], w, raster x, raster y}]
+ * with the vertex record {pos[3], n[3], alpha[3], p, material, prim, dir_pdf}; entries the CUDA path does
+ * not keep (p, prim) are NaN.  Returns the number of doubles the full record needs via *n_out. */
+int bdpt_trace_sample(BdptContext* ctx, const BdptRenderParams* p, int x, int y, int sample, double* out, size_t cap,
+                      size_t* n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BDPT_B200_H */
