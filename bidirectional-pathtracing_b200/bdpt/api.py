@@ -50,7 +50,7 @@ EXPORTS = ["bdpt_create", "bdpt_destroy", "bdpt_last_error", "bdpt_set_stream", 
            "bdpt_set_camera", "bdpt_set_frame", "bdpt_clear", "bdpt_render", "bdpt_read_framebuffer",
            "bdpt_framebuffer_device", "bdpt_tonemap_rgba8", "bdpt_get_stats", "bdpt_intersect_batch",
            "bdpt_occluded_batch", "bdpt_bsdf_eval_batch", "bdpt_bsdf_sample_batch", "bdpt_light_eval_batch",
-           "bdpt_camera_eval_batch", "bdpt_trace_sample"]
+           "bdpt_camera_eval_batch", "bdpt_trace_sample", "bdpt_host_build_bvh"]
 
 _lib = None
 
@@ -84,6 +84,8 @@ def load_library():
     L.bdpt_occluded_batch.argtypes = [vp, dp, C.c_size_t, C.POINTER(C.c_int32)]
     L.bdpt_trace_sample.argtypes = [vp, C.POINTER(RenderParams), C.c_int, C.c_int, C.c_int, dp, C.c_size_t,
                                     C.POINTER(C.c_size_t)]
+    u32p = C.POINTER(C.c_uint32)
+    L.bdpt_host_build_bvh.argtypes = [vp, C.c_uint32, u32p, C.c_uint32, u32p, u32p, u32p]
     for name in EXPORTS:
         if name not in ("bdpt_destroy", "bdpt_last_error"):
             getattr(L, name).restype = C.c_int
@@ -229,3 +231,21 @@ class Renderer:
         verts = out[2:2 + 13 * (ne + nl)].reshape(-1, 13)
         strat = out[2 + 13 * (ne + nl):].reshape(-1, 8)
         return {"eye": verts[:ne], "light": verts[ne:], "strategies": strat}
+
+
+def host_build_bvh(scene: fs.FlatScene):
+    """Host-only: (nodes as (n,20) uint32, prim_order, max_depth) of the BVH bdpt_upload_scene would build."""
+    L = load_library()
+    prims = np.ascontiguousarray(scene.prims)
+    n_nodes, depth = C.c_uint32(), C.c_uint32()
+    rc = L.bdpt_host_build_bvh(prims.ctypes.data, len(prims), None, 0, C.byref(n_nodes), None, C.byref(depth))
+    if rc != 0:
+        raise BdptError(f"bdpt_host_build_bvh failed ({rc})")
+    nodes = np.zeros((n_nodes.value, 20), np.uint32)
+    order = np.zeros(len(prims), np.uint32)
+    u32p = C.POINTER(C.c_uint32)
+    rc = L.bdpt_host_build_bvh(prims.ctypes.data, len(prims), nodes.ctypes.data_as(u32p), n_nodes.value, C.byref(n_nodes),
+                               order.ctypes.data_as(u32p), C.byref(depth))
+    if rc != 0:
+        raise BdptError(f"bdpt_host_build_bvh failed ({rc})")
+    return nodes, order, depth.value

@@ -33,6 +33,7 @@ struct BdptContext {
   DScene sc{};
   uint4* d_nodes = nullptr;
   float4 *d_prims = nullptr, *d_shading = nullptr, *d_mats = nullptr, *d_lights = nullptr;
+  double* d_prims64 = nullptr;
   uint32_t bvh_nodes = 0, bvh_depth = 0;
   double ms_bvh_build = 0;
 
@@ -110,6 +111,25 @@ void make_dcamera(const BdptCamera& c, int W, int H, DCamera* out) {
   out->W = W; out->H = H;
 }
 
+// fp32 bounds of what the kernels actually test: the fp32-narrowed triangle, a slightly padded sphere
+void make_build_prims(const BdptPrim* prims, uint32_t n_prims, std::vector<BuildPrim>* out) {
+  std::vector<BuildPrim>& bp = *out;
+  bp.resize(n_prims);
+  for (uint32_t i = 0; i < n_prims; i++) {
+    const double* d = prims[i].data;
+    if (prims[i].type == BDPT_PRIM_TRIANGLE) {
+      for (int a = 0; a < 3; a++) {
+        float v0 = (float)d[a], v1 = (float)d[3 + a], v2 = (float)d[6 + a];
+        bp[i].lo[a] = std::min(v0, std::min(v1, v2));
+        bp[i].hi[a] = std::max(v0, std::max(v1, v2));
+      }
+    } else {
+      double r = std::fabs(d[3]) * (1.0 + 1e-6) + 1e-7;
+      for (int a = 0; a < 3; a++) { bp[i].lo[a] = f_down(d[a] - r); bp[i].hi[a] = f_up(d[a] + r); }
+    }
+  }
+}
+
 int ensure_batch_storage(BdptContext* ctx, size_t B, int m, size_t qcap) {
   if (B > ctx->cap_B || m > ctx->cap_m) {
     dfree(ctx->v0); dfree(ctx->v1); dfree(ctx->v2); dfree(ctx->v3); dfree(ctx->counts);
@@ -146,7 +166,8 @@ void fill_job(BdptContext* ctx, const BdptRenderParams* p, Job* J) {
   J->v0 = ctx->v0; J->v1 = ctx->v1; J->v2 = ctx->v2; J->v3 = ctx->v3; J->counts = ctx->counts;
   J->q0 = ctx->q0; J->q1 = ctx->q1; J->q2 = ctx->q2; J->qctr = ctx->qctr; J->qcap = (unsigned int)ctx->cap_q;
   J->acc_eye = ctx->acc_eye; J->acc_light = ctx->acc_light; J->stats = ctx->d_stats; J->dbg = nullptr;
-  J->seed = p->seed; J->m = p->max_ray_depth; J->first_sample = p->first_sample;
+  // the walk stores a vertex before it tests the depth (bidirection.cpp:82-86): m = 0 behaves as m = 1
+  J->seed = p->seed; J->m = std::max(1, p->max_ray_depth); J->first_sample = p->first_sample;
   J->tiles_x = (ctx->W + 7) / 8;
   J->npix_pad = J->tiles_x * ((ctx->H + 3) / 4) * 32;
   J->roulette = (p->flags & BDPT_FLAG_ROULETTE) ? 1 : 0;
@@ -230,7 +251,7 @@ void bdpt_destroy(BdptContext* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  dfree(ctx->d_nodes); dfree(ctx->d_prims); dfree(ctx->d_shading); dfree(ctx->d_mats); dfree(ctx->d_lights);
+  dfree(ctx->d_nodes); dfree(ctx->d_prims); dfree(ctx->d_shading); dfree(ctx->d_mats); dfree(ctx->d_lights); dfree(ctx->d_prims64);
   dfree(ctx->acc_eye); dfree(ctx->acc_light); dfree(ctx->resolve_tmp); dfree(ctx->rgba_tmp);
   dfree(ctx->v0); dfree(ctx->v1); dfree(ctx->v2); dfree(ctx->v3); dfree(ctx->counts);
   dfree(ctx->q0); dfree(ctx->q1); dfree(ctx->q2); dfree(ctx->qctr); dfree(ctx->d_stats);
@@ -269,20 +290,8 @@ int bdpt_upload_scene(BdptContext* ctx, const BdptCamera* camera, const BdptMate
   }
 
   auto t0 = std::chrono::steady_clock::now();
-  std::vector<BuildPrim> bp(n_prims);
-  for (uint32_t i = 0; i < n_prims; i++) {
-    const double* d = prims[i].data;
-    if (prims[i].type == BDPT_PRIM_TRIANGLE) {
-      for (int a = 0; a < 3; a++) {
-        float v0 = (float)d[a], v1 = (float)d[3 + a], v2 = (float)d[6 + a];  // the fp32 triangle the kernel tests
-        bp[i].lo[a] = std::min(v0, std::min(v1, v2));
-        bp[i].hi[a] = std::max(v0, std::max(v1, v2));
-      }
-    } else {
-      double r = std::fabs(d[3]) * (1.0 + 1e-6) + 1e-7;
-      for (int a = 0; a < 3; a++) { bp[i].lo[a] = f_down(d[a] - r); bp[i].hi[a] = f_up(d[a] + r); }
-    }
-  }
+  std::vector<BuildPrim> bp;
+  make_build_prims(prims, n_prims, &bp);
   Bvh8 bvh;
   build_bvh8(bp, &bvh);
   ctx->ms_bvh_build = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -290,10 +299,12 @@ int bdpt_upload_scene(BdptContext* ctx, const BdptCamera* camera, const BdptMate
 
   // leaf-ordered primitive + shading records
   std::vector<float4> hp(3 * (size_t)std::max<uint32_t>(n_prims, 1)), hs(3 * (size_t)std::max<uint32_t>(n_prims, 1));
+  std::vector<double> h64(10 * (size_t)std::max<uint32_t>(n_prims, 1), 0.0);
   for (size_t k = 0; k < bvh.prim_order.size(); k++) {
     uint32_t id = bvh.prim_order[k];
     const BdptPrim& p = prims[id];
     const double* d = p.data;
+    for (int a = 0; a < 9; a++) h64[10 * k + a] = d[a];  // triangle p1 p2 p3 / sphere centre, radius
     if (p.type == BDPT_PRIM_TRIANGLE) {
       float v0[3], v1[3], v2[3];
       for (int a = 0; a < 3; a++) { v0[a] = (float)d[a]; v1[a] = (float)d[3 + a]; v2[a] = (float)d[6 + a]; }
@@ -333,10 +344,12 @@ int bdpt_upload_scene(BdptContext* ctx, const BdptCamera* camera, const BdptMate
   }
 
   CK(cudaStreamSynchronize(ctx->stream));
-  dfree(ctx->d_nodes); dfree(ctx->d_prims); dfree(ctx->d_shading); dfree(ctx->d_mats); dfree(ctx->d_lights);
+  dfree(ctx->d_nodes); dfree(ctx->d_prims); dfree(ctx->d_shading); dfree(ctx->d_mats); dfree(ctx->d_lights); dfree(ctx->d_prims64);
   CK(cudaMalloc(&ctx->d_nodes, bvh.nodes.size() * sizeof(uint32_t)));
   CK(cudaMalloc(&ctx->d_prims, hp.size() * sizeof(float4)));
   CK(cudaMalloc(&ctx->d_shading, hs.size() * sizeof(float4)));
+  CK(cudaMalloc(&ctx->d_prims64, h64.size() * sizeof(double)));
+  CK(cudaMemcpyAsync(ctx->d_prims64, h64.data(), h64.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMalloc(&ctx->d_mats, hm.size() * sizeof(float4)));
   CK(cudaMalloc(&ctx->d_lights, hl.size() * sizeof(float4)));
   CK(cudaMemcpyAsync(ctx->d_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -346,7 +359,7 @@ int bdpt_upload_scene(BdptContext* ctx, const BdptCamera* camera, const BdptMate
   CK(cudaMemcpyAsync(ctx->d_lights, hl.data(), hl.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
 
-  ctx->sc.nodes = ctx->d_nodes; ctx->sc.prims = ctx->d_prims; ctx->sc.shading = ctx->d_shading;
+  ctx->sc.nodes = ctx->d_nodes; ctx->sc.prims = ctx->d_prims; ctx->sc.shading = ctx->d_shading; ctx->sc.prims64 = ctx->d_prims64;
   ctx->sc.materials = ctx->d_mats; ctx->sc.lights = ctx->d_lights;
   ctx->sc.n_lights = (int)n_lights; ctx->sc.n_materials = (int)n_materials;
   ctx->sc.n_nodes = (int)(bvh.nodes.size() / 20); ctx->sc.n_prims = (int)n_prims;
@@ -407,7 +420,7 @@ int bdpt_render(BdptContext* ctx, const BdptRenderParams* p) {
 
   Job J;
   // batch size: bounded by the vertex planes (64 B/vertex) and the worst-case shadow queue (48 B/entry)
-  const int m = p->max_ray_depth;
+  const int m = std::max(1, p->max_ray_depth);
   const size_t per_sample = (size_t)2 * (m + 1) * 64 + (size_t)(m + 1) * (m + 1) * 48 + 8;
   size_t B = (size_t)(3ull << 30) / per_sample;
   B = std::min<size_t>(B, 1u << 20);
@@ -500,6 +513,24 @@ int bdpt_get_stats(BdptContext* ctx, BdptStats* out) {
 }
 
 // ------------------------------------------------------------------------------------ test hooks
+int bdpt_host_build_bvh(const BdptPrim* prims, uint32_t n_prims, uint32_t* nodes_out, uint32_t nodes_cap,
+                        uint32_t* n_nodes, uint32_t* prim_order_out, uint32_t* max_depth) {
+  if (!prims && n_prims) return BDPT_ERR_ARG;
+  std::vector<BuildPrim> bp;
+  make_build_prims(prims, n_prims, &bp);
+  Bvh8 bvh;
+  build_bvh8(bp, &bvh);
+  uint32_t nn = (uint32_t)(bvh.nodes.size() / 20);
+  if (n_nodes) *n_nodes = nn;
+  if (max_depth) *max_depth = bvh.max_depth;
+  if (nodes_out) {
+    if (nodes_cap < nn) return BDPT_ERR_ARG;
+    memcpy(nodes_out, bvh.nodes.data(), bvh.nodes.size() * sizeof(uint32_t));
+  }
+  if (prim_order_out) memcpy(prim_order_out, bvh.prim_order.data(), bvh.prim_order.size() * sizeof(uint32_t));
+  return BDPT_OK;
+}
+
 int bdpt_intersect_batch(BdptContext* ctx, const double* rays, size_t n, double* hits) {
   int rc = check_ready(ctx, false);
   if (rc) return rc;
@@ -585,7 +616,7 @@ int bdpt_trace_sample(BdptContext* ctx, const BdptRenderParams* p, int x, int y,
   if (rc) return rc;
   if (!p || !out || x < 0 || y < 0 || x >= ctx->W || y >= ctx->H) return fail(ctx, BDPT_ERR_ARG, "bad trace arguments");
   CK(cudaSetDevice(ctx->device));
-  const int m = p->max_ray_depth;
+  const int m = std::max(1, p->max_ray_depth);
   const size_t B = 1024;
   rc = ensure_batch_storage(ctx, B, m, B * (size_t)(m + 1) * (size_t)(m + 1));
   if (rc) return rc;

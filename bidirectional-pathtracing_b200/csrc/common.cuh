@@ -91,6 +91,7 @@ struct DScene {
   const uint4* nodes;       // Node8 as 5 x uint4
   const float4* prims;      // leaf-ordered primitive records, 3 x float4 each
   const float4* shading;    // leaf-ordered shading normals n1,n2,n3, 3 x float4 each
+  const double* prims64;    // leaf-ordered fp64 geometry, 10 doubles each: triangle p1 p2 p3 (+pad) / sphere c, r
   const float4* materials;  // DMaterial as 5 x float4
   const float4* lights;     // DLight as 5 x float4
   int n_lights;

@@ -122,9 +122,8 @@ __global__ void __launch_bounds__(128) k_walk(const Job J) {
     Hit h = traverse<false>(sc, o, d, tmin, tmax);
     nrays++;
     if (h.leaf < 0) break;
-    f3 n; int prim, mat;
-    finish_hit(sc, h, o, d, &n, &prim, &mat);
-    const f3 hit_p = o + d * h.t;
+    f3 n, hit_p; int prim, mat;
+    finish_hit(sc, h, o, d, &n, &prim, &mat, &hit_p);
     const Frame fr = make_frame(n);
     const f3 w_out = fr.to_local(-d);
     const Mat M = load_mat(sc, mat);
@@ -410,8 +409,8 @@ __global__ void k_intersect_batch(DScene sc, const float* rays, size_t n, float*
   Hit h = traverse<false>(sc, o, d, r[6], r[7]);
   float* q = out + 6 * i;
   if (h.leaf < 0) { q[0] = -1.f; q[1] = INFINITY; q[2] = q[3] = q[4] = 0.f; q[5] = -1.f; return; }
-  f3 nn; int prim, mat;
-  finish_hit(sc, h, o, d, &nn, &prim, &mat);
+  f3 nn, hp; int prim, mat;
+  finish_hit(sc, h, o, d, &nn, &prim, &mat, &hp);
   q[0] = __int_as_float(prim); q[1] = h.t; q[2] = nn.x; q[3] = nn.y; q[4] = nn.z; q[5] = __int_as_float(mat);
 }
 

@@ -148,19 +148,62 @@ __device__ inline Hit traverse(const DScene& sc, f3 o, f3 d, float tmin, float t
 
 // Shading data of an accepted closest hit: interpolated (unflipped) unit normal, primitive id in
 // the reference's order and material id (Triangle::intersect triangle.cpp:80-87, Sphere :78-87).
-__device__ inline void finish_hit(const DScene& sc, const Hit& h, f3 o, f3 d, f3* n, int* prim_id, int* mat) {
+//
+// The winner of the fp32 traversal is re-intersected ONCE in fp64 against the fp64 geometry the
+// loader delivered (B200 has full-rate-class FP64 units; this is ~60 DFMA per ray, not per test):
+// t and the barycentrics then agree with the fp64 reference to ~1e-12 relative instead of the
+// ~1e-4 an fp32 Moller-Trumbore gives at grazing incidence, which keeps hit points on their
+// surface and the EPS_F = 1e-5 self-intersection offsets meaningful.
+__device__ inline void finish_hit(const DScene& sc, Hit& h, f3 o, f3 d, f3* n, int* prim_id, int* mat, f3* hit_p) {
   float4 a = ldg4(sc.prims + 3 * h.leaf), b = ldg4(sc.prims + 3 * h.leaf + 1);
   *prim_id = __float_as_int(a.w);
   int mw = __float_as_int(b.w);
   *mat = mw & 0x7fffffff;
+  const double* g = sc.prims64 + 10 * (size_t)h.leaf;
+  const double ox = o.x, oy = o.y, oz = o.z, dx = d.x, dy = d.y, dz = d.z;
   if (mw >= 0) {
+    const double2 g0 = __ldg((const double2*)g), g1 = __ldg((const double2*)g + 1), g2 = __ldg((const double2*)g + 2),
+                  g3 = __ldg((const double2*)g + 3), g4 = __ldg((const double2*)g + 4);
+    const double p1x = g0.x, p1y = g0.y, p1z = g1.x;
+    const double e1x = g1.y - p1x, e1y = g2.x - p1y, e1z = g2.y - p1z;
+    const double e2x = g3.x - p1x, e2y = g3.y - p1y, e2z = g4.x - p1z;
+    const double sx = ox - p1x, sy = oy - p1y, sz = oz - p1z;
+    const double s1x = dy * e2z - dz * e2y, s1y = dz * e2x - dx * e2z, s1z = dx * e2y - dy * e2x;
+    const double s2x = sy * e1z - sz * e1y, s2y = sz * e1x - sx * e1z, s2z = sx * e1y - sy * e1x;
+    const double inv = 1.0 / (s1x * e1x + s1y * e1y + s1z * e1z);
+    const double t = (s2x * e2x + s2y * e2y + s2z * e2z) * inv;
+    const double b1 = (s1x * sx + s1y * sy + s1z * sz) * inv;
+    const double b2 = (s2x * dx + s2y * dy + s2z * dz) * inv;
+    if (t == t && fabs(t - (double)h.t) <= 1e-3 * fabs((double)h.t)) {  // sanity: same root
+      h.t = (float)t; h.b1 = (float)b1; h.b2 = (float)b2;
+      *hit_p = mk3((float)(ox + dx * t), (float)(oy + dy * t), (float)(oz + dz * t));
+    } else {
+      *hit_p = o + d * h.t;
+    }
     float4 n1 = ldg4(sc.shading + 3 * h.leaf), n2 = ldg4(sc.shading + 3 * h.leaf + 1), n3 = ldg4(sc.shading + 3 * h.leaf + 2);
     float b0 = 1.f - h.b1 - h.b2;
     f3 nn = mk3(n1.x, n1.y, n1.z) * b0 + h.b1 * mk3(n2.x, n2.y, n2.z) + h.b2 * mk3(n3.x, n3.y, n3.z);
     *n = normalized(nn);
   } else {
-    f3 p = o + h.t * d;
-    *n = normalized(p - mk3(a.x, a.y, a.z));
+    const double2 g0 = __ldg((const double2*)g), g1 = __ldg((const double2*)g + 1);
+    const double cx = g0.x, cy = g0.y, cz = g1.x, r = g1.y;
+    const double ocx = ox - cx, ocy = oy - cy, ocz = oz - cz;
+    const double A = dx * dx + dy * dy + dz * dz, hb = ocx * dx + ocy * dy + ocz * dz;
+    const double k = hb / A;
+    const double lx = ocx - dx * k, ly = ocy - dy * k, lz = ocz - dz * k;
+    const double disc = A * (r * r - (lx * lx + ly * ly + lz * lz));
+    double t = (double)h.t;
+    if (disc >= 0.0) {
+      const double sd = sqrt(disc);
+      const double t1 = (-hb - sd) / A, t2 = (-hb + sd) / A;
+      t = fabs(t1 - t) <= fabs(t2 - t) ? t1 : t2;  // the root the fp32 test picked
+    }
+    h.t = (float)t;
+    const double px = ox + dx * t, py = oy + dy * t, pz = oz + dz * t;
+    *hit_p = mk3((float)px, (float)py, (float)pz);
+    const double nx = px - cx, ny = py - cy, nz = pz - cz;
+    const double il = 1.0 / sqrt(nx * nx + ny * ny + nz * nz);
+    *n = mk3((float)(nx * il), (float)(ny * il), (float)(nz * il));
   }
 }
 

@@ -107,6 +107,12 @@ int bdpt_tonemap_rgba8(BdptContext* ctx, int which, uint8_t* rgba_out);
 int bdpt_get_stats(BdptContext* ctx, BdptStats* out);
 
 /* --- test hooks (parity against the oracle) ------------------------------------------------ */
+/* Host-only (needs no GPU): builds the 8-wide BVH exactly as bdpt_upload_scene does and returns it for
+ * inspection — 20 words per node (layout: bidirectional-pathtracing_b200/csrc/bvh8.h), the leaf order
+ * (prim_order_out[k] = primitive index of leaf slot k, n_prims entries) and the tree depth.  Pass
+ * nodes_out = NULL to query n_nodes first.  Stands where BVHAccel::construct_bvh does (bvh.cpp:51-129). */
+int bdpt_host_build_bvh(const BdptPrim* prims, uint32_t n_prims, uint32_t* nodes_out, uint32_t nodes_cap,
+                        uint32_t* n_nodes, uint32_t* prim_order_out, uint32_t* max_depth);
 /* rays: n x {o[3], d[3], tmin, tmax} fp64 -> hits: n x {prim id (-1 miss), t, n[3], material} fp64.
  * Mirrors BVHAccel::intersect (bvh.h:104-107). */
 int bdpt_intersect_batch(BdptContext* ctx, const double* rays, size_t n, double* hits);

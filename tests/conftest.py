@@ -7,6 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "bidirectional-pathtracing_b200"))
 
+ROOT_DIR = ROOT
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 

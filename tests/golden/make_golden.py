@@ -14,6 +14,7 @@ Writes:
                             sample_ray_pdf batch (480x360)
   <name>.render.npz         reference `-t 1` render (fp64 sum / eye / light buffers, ray count)
   CBspheres_lambertian.strategies.npz   reference per-(t,s) images (debug filter of bidirection.cpp:492-493)
+  <name>.converged.npz      reference render at 1024 spp, 64x48, all host threads (statistical pin)
 """
 import os
 import sys
@@ -91,6 +92,14 @@ def main():
         np.savez_compressed(os.path.join(OUT, name + ".render.npz"), sum=s, eye=e, light=l,
                             params=np.array([W, H, ns, m]), rays=np.array([info["rays"]]))
         print(name, "prims", sc.n_prims, "render rays", info["rays"])
+
+    # converged reference renders (the reference's own binary, all host threads): the level-3 pin
+    for name, (W, H, ns, m) in {"CBspheres_lambertian": (64, 48, 1024, 5), "CBspheres": (64, 48, 1024, 5),
+                                "CBgems": (64, 48, 1024, 5)}.items():
+        s, e, l, info = O.ref_render(O.ref_scene(name), W, H, ns, m, threads=os.cpu_count())
+        np.savez_compressed(os.path.join(OUT, name + ".converged.npz"), sum=s.astype(np.float32), eye=e.astype(np.float32),
+                            light=l.astype(np.float32), params=np.array([W, H, ns, m]))
+        print(name, "converged", info)
 
     # per-strategy images, small
     name, (W, H, ns, m) = "CBspheres_lambertian", (32, 24, 2, 3)

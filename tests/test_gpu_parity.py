@@ -1,0 +1,298 @@
+"""Parity of the CUDA path (through the C-ABI, libbdpt_b200.so) against the fp64 oracle port and
+the golden fixtures produced by the reference itself.  All tests need a B200: `-m gpu`.
+
+Tolerances (stated once, used below):
+  * hit primitive / material ids: bit-exact, except rays whose two nearest candidate hits are
+    within 1e-5 relative of each other in the oracle (tie band) — none occur in the fixtures
+  * hit t, normal; BSDF f / pdf; light Le / pdfs; camera ray / We / pdf: 1e-5 relative (north_star)
+  * per-sample contributions with identical random numbers: 1e-3 relative for >= 97% of strategies
+    (the rest are fp32/fp64 discrete divergences: a different primitive hit near an edge)
+  * images with identical random numbers: relMSE <= 1e-3; converged images against the reference's
+    own render: relMSE <= 1e-2 (the reference's Monte-Carlo noise floor at the fixture's spp)
+relMSE = mean((a-b)^2 / (b^2 + 1e-2)) on linear RGB.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ALL_SCENES, GOLDEN, load_scene
+
+pytestmark = pytest.mark.gpu
+
+
+def relmse(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.mean((a - b) ** 2 / (b ** 2 + 1e-2)))
+
+
+@pytest.fixture(scope="module")
+def api():
+    from bdpt import api as A
+    A.load_library()
+    return A
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+def make_renderer(api, name, w, h, **kw):
+    R = api.Renderer(0, **kw)
+    R.set_scene(load_scene(name))
+    R.set_frame_size(w, h)
+    return R
+
+
+# ---------------------------------------------------------------------------------- level 1: rays
+@pytest.mark.parametrize("name", ALL_SCENES)
+def test_hit_ids_t_normals_match_reference(api, O, name):
+    g = np.load(os.path.join(GOLDEN, name + ".units.npz"))
+    R = make_renderer(api, name, 480, 360)
+    got, ref = R.intersect(g["rays"]), g["hits"]
+    same = got[:, 0] == ref[:, 0]
+    if not same.all():
+        # only near-ties may differ: the oracle's runner-up must be within 1e-5 relative of its best
+        bad = np.where(~same)[0]
+        br = O.Oracle(load_scene(name)).intersect_brute(g["rays"][bad])
+        assert np.all(np.abs(br[:, 2] - br[:, 1]) <= 1e-5 * np.abs(br[:, 1])), f"{len(bad)} hit ids differ outside the tie band"
+    hit = same & (ref[:, 0] >= 0)
+    assert hit.sum() > 500
+    assert np.array_equal(got[hit, 5], ref[hit, 5])
+    assert np.max(np.abs(got[hit, 1] - ref[hit, 1]) / ref[hit, 1]) <= 1e-5
+    assert np.max(np.abs(got[hit, 2:5] - ref[hit, 2:5])) <= 1e-5
+    # any-hit (shadow) traversal agrees with closest-hit on the same segments
+    occ = R.occluded(g["rays"])
+    assert np.array_equal(occ > 0, ref[:, 0] >= 0)
+
+
+def test_ray_edge_cases(api, O):
+    """Empty batch, zero-length and inverted intervals, axis-parallel rays, rays starting on a surface."""
+    name = "CBspheres"
+    R = make_renderer(api, name, 64, 48)
+    orc = O.Oracle(load_scene(name))
+    assert R.intersect(np.zeros((0, 8))).shape == (0, 6)
+    eps = float(np.float32(1e-5))
+    rays = np.array([
+        [0, 0.75, 0.5, 0, 0, -1, eps, np.inf],        # axis-parallel (two zero direction components)
+        [0, 0.75, 0.5, 0, -1, 0, eps, np.inf],
+        [0, 0.75, 0.5, 1, 0, 0, eps, np.inf],
+        [0, 0.75, 0.5, 0, 0, -1, eps, 0.1],            # interval ends before the wall
+        [0, 0.75, 0.5, 0, 0, -1, 5.0, 1.0],            # inverted interval: nothing
+        [0, 0.0, 0.0, 0, 1, 0, eps, np.inf],           # starts on the floor, leaves it
+        [0, 0.0, 0.0, 0.6, 0.8, 0, eps, np.inf],
+        [0, 0.75, 10.0, 0, 0, -1, 0.1, 100.0],         # camera-like clip range
+        [0, 5.0, 0.0, 0, 1, 0, eps, np.inf],           # outside, pointing away: miss
+    ], np.float64)
+    got, ref = R.intersect(rays), orc.intersect(rays)
+    assert np.array_equal(got[:, 0], ref[:, 0])
+    h = ref[:, 0] >= 0
+    assert np.allclose(got[h, 1], ref[h, 1], rtol=1e-5)
+
+
+# ------------------------------------------------------------------------ level 1b: shading units
+@pytest.mark.parametrize("name", ["CBspheres_lambertian", "CBspheres", "CBgems", "CBbunny"])
+def test_bsdf_light_camera_match_reference(api, name):
+    g = np.load(os.path.join(GOLDEN, name + ".units.npz"))
+    w, h = map(int, g["cam_wh"])
+    R = make_renderer(api, name, w, h)
+    a, b = R.bsdf_eval(g["bsdf_in"]), g["bsdf_out"]
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    assert np.allclose(a, b, rtol=1e-5, atol=1e-6, equal_nan=True)
+    a, b = R.light_eval(g["light_in"]), g["light_out"]
+    assert np.array_equal(a[:, 0], b[:, 0])
+    assert np.allclose(a, b, rtol=1e-5, atol=1e-6)
+    a, b = R.camera_eval(g["cam_in"]), g["cam_out"]
+    assert np.allclose(a[:, :6], b[:, :6], rtol=1e-5, atol=1e-6)       # generate_ray
+    assert np.allclose(a[:, 6], b[:, 6], rtol=1e-4, atol=1e-6)         # We (cos^4: four roundings)
+    assert np.allclose(a[:, 7], b[:, 7], rtol=1e-5) and np.allclose(a[:, 10], b[:, 10], rtol=1e-5)
+    assert np.mean(np.all(a[:, 8:10] == b[:, 8:10], axis=1)) >= 0.995     # raster pixel (boundary cases)
+
+
+@pytest.mark.parametrize("name", ["CBspheres", "CBgems", "CBspheres_lambertian"])
+def test_bsdf_sample_f_matches_oracle(api, O, name):
+    sc = load_scene(name)
+    R = make_renderer(api, name, 64, 48)
+    orc = O.Oracle(sc)
+    rng = np.random.default_rng(5)
+    n = 4000
+    q = np.zeros((n, 7))
+    q[:, 0] = rng.integers(0, len(sc.materials), n)
+    w = rng.normal(size=(n, 3)); q[:, 1:4] = w / np.linalg.norm(w, axis=1, keepdims=True)
+    q[:, 4:7] = (np.floor(rng.uniform(0, 1, (n, 3)) * 2 ** 23) + 0.5) / 2 ** 23   # the generator's lattice
+    a, b = R.bsdf_sample(q), orc.bsdf_sample(q)
+    # glass: near R == coin the fp32 and fp64 Schlick terms can pick different lobes; exclude those
+    agree = np.abs(a[:, 3] - b[:, 3]) <= 1e-4 * np.maximum(1.0, np.abs(b[:, 3]))
+    assert agree.mean() > 0.999
+    assert np.allclose(a[agree, :3], b[agree, :3], atol=2e-6)
+    assert np.allclose(a[agree, 4:], b[agree, 4:], rtol=2e-4, atol=1e-5)
+
+
+# ----------------------------------------------------------------- level 2: per-sample, per-strategy
+@pytest.mark.parametrize("name,m", [("CBspheres_lambertian", 5), ("CBspheres", 5), ("CBgems", 8), ("CBbunny", 5)])
+def test_single_samples_match_oracle(api, O, name, m):
+    """Same random numbers on both sides: vertices and every strategy's weighted contribution agree."""
+    W, H, ns = 64, 48, 4
+    R = make_renderer(api, name, W, H, ns_aa=ns, max_ray_depth=m, seed=3)
+    orc = O.Oracle(load_scene(name), W, H)
+    rng = np.random.default_rng(1)
+    n_strat = n_bad = n_div = 0
+    for _ in range(60):
+        x, y, k = int(rng.integers(W)), int(rng.integers(H)), int(rng.integers(ns))
+        tg = R.trace_sample(x, y, k)
+        to = orc.trace_sample(ns, m, x, y, k, seed=3)
+        ne, nl = min(len(tg["eye"]), len(to["eye"])), min(len(tg["light"]), len(to["light"]))
+        dv = 0.0
+        if ne > 2: dv = max(dv, np.nanmax(np.abs(tg["eye"][2:ne, :6] - to["eye"][2:ne, :6])))
+        if nl > 1: dv = max(dv, np.nanmax(np.abs(tg["light"][1:nl, :6] - to["light"][1:nl, :6])))
+        if dv > 1e-3:
+            n_div += 1          # the two walks hit different primitives somewhere (fp32 vs fp64 near an edge)
+            continue
+        # vertices the CUDA path did not store have zero throughput in the oracle
+        assert np.all(to["eye"][len(tg["eye"]):, 6:9] == 0) and np.all(to["light"][len(tg["light"]):, 6:9] == 0)
+        so = {(int(r[0]), int(r[1])): r for r in to["strategies"]}
+        for r in tg["strategies"]:
+            q = so[(int(r[0]), int(r[1]))]
+            g_ill = np.zeros(3) if np.isnan(r[2]) else r[2:5] * r[5]
+            o_ill = np.zeros(3) if np.isnan(q[2]) else q[2:5] * q[5]
+            n_strat += 1
+            if np.abs(g_ill - o_ill).max() > 1e-3 * (np.abs(o_ill).max() + 1e-2):
+                n_bad += 1
+            elif not np.isnan(r[2]) and not np.isnan(q[2]) and np.abs(o_ill).max() > 0:
+                assert (r[6], r[7]) == (q[6], q[7]) or r[0] != 1   # light-image raster pixel
+    assert n_div <= 3
+    assert n_strat > 800 and n_bad <= 0.03 * n_strat, (n_bad, n_strat)
+
+
+def test_strategy_images_match_oracle(api, O):
+    """Each (s,t) strategy image against the oracle's, identical random numbers (north_star level 2)."""
+    name, W, H, ns, m = "CBspheres", 48, 36, 16, 3
+    R = make_renderer(api, name, W, H, ns_aa=ns, max_ray_depth=m, seed=21)
+    orc = O.Oracle(load_scene(name), W, H)
+    nonzero = 0
+    for t in range(1, m + 2):
+        for s in range(0, m + 2):
+            R.clear(); R.render(strategy=(t, s))
+            got = R.framebuffer(0)
+            ref = orc.render(ns, m, rng_mode=1, seed=21, threads=8, strategy=(t, s))[0]
+            assert abs(got.mean() - ref.mean()) <= 2e-3 * ref.mean() + 1e-6, (t, s)
+            assert relmse(got, ref) <= 1e-3, (t, s)
+            nonzero += ref.any()
+    assert nonzero >= 12
+
+
+# ------------------------------------------------------------------------------- level 3: images
+@pytest.mark.parametrize("name,m,roulette", [("CBspheres_lambertian", 5, 0), ("CBspheres", 5, 0), ("CBgems", 16, 0),
+                                              ("CBbunny", 5, 0), ("CBspheres_lambertian_occluded", 4, 0),
+                                              ("CBspheres", 6, 1)])
+def test_render_matches_oracle_same_random_numbers(api, O, name, m, roulette):
+    W, H, ns = 64, 48, 8
+    R = make_renderer(api, name, W, H, ns_aa=ns, max_ray_depth=m, seed=11, roulette=bool(roulette))
+    R.render()
+    gs, ge, gl = (R.framebuffer(i).astype(np.float64) for i in range(3))
+    os_, oe, ol, _ = O.Oracle(load_scene(name), W, H).render(ns, m, rng_mode=1, seed=11, threads=8, roulette=roulette)
+    assert np.isfinite(gs).all()
+    assert np.allclose(gs, ge + gl, rtol=1e-5, atol=1e-6)          # sampleBuffer = eye + light
+    assert abs(gs.mean() - os_.mean()) <= 1e-3 * os_.mean()
+    assert relmse(gs, os_) <= 1e-3 and relmse(ge, oe) <= 1e-3 and relmse(gl, ol) <= 1e-3
+    close = np.all(np.abs(gs - os_) <= 1e-3 * (np.abs(os_) + 1e-2), axis=-1)
+    assert close.mean() >= 0.95
+
+
+@pytest.mark.parametrize("name", ["CBspheres_lambertian", "CBspheres", "CBgems"])
+def test_converged_image_matches_reference_render(api, name):
+    """Against the reference's OWN converged render (tests/golden/*.converged.npz, made by the
+    reference binary with its own mt19937 streams): independent random numbers, so the bound is
+    the reference's noise floor."""
+    g = np.load(os.path.join(GOLDEN, name + ".converged.npz"))
+    W, H, ns_ref, m = map(int, g["params"])
+    R = make_renderer(api, name, W, H, ns_aa=4096, max_ray_depth=m, seed=1)
+    R.render()
+    got = R.framebuffer(0)
+    ref = g["sum"]
+    assert abs(got.mean() - ref.mean()) <= 5e-3 * ref.mean()
+    assert relmse(got, ref) <= 1e-2
+    # equal-spp noise is no worse than the reference's: compare both against the 4096-spp CUDA image
+    R2 = make_renderer(api, name, W, H, ns_aa=ns_ref, max_ray_depth=m, seed=99)
+    R2.render()
+    noise_gpu = relmse(R2.framebuffer(0), got)
+    noise_ref = relmse(ref, got)
+    assert noise_gpu <= 1.25 * noise_ref + 1e-5
+
+
+# ----------------------------------------------------------- properties at BASELINE.json sizes
+def test_config1_full_size_properties(api):
+    """configs[0]: CBspheres_lambertian 480x360, 4 spp, m=5 — sharding by sample index is exact,
+    the image is seed-deterministic, finite, and sum = eye + light."""
+    name, W, H, ns, m = "CBspheres_lambertian", 480, 360, 4, 5
+    A = make_renderer(api, name, W, H, ns_aa=ns, max_ray_depth=m, seed=5)
+    A.render()
+    full = [A.framebuffer(i) for i in range(3)]
+    st = A.stats()
+    assert st["samples"] == W * H * ns and st["rays_closest"] > 0 and st["rays_shadow"] > 0
+    B = make_renderer(api, name, W, H, ns_aa=ns, max_ray_depth=m, seed=5)
+    B.render(first_sample=0, n_samples=1)
+    B.render(first_sample=1, n_samples=3)     # two shards accumulate into the same frame
+    parts = [B.framebuffer(i) for i in range(3)]
+    for f, p in zip(full, parts):
+        assert np.isfinite(f).all()
+        assert np.allclose(f, p, rtol=2e-5, atol=1e-6)   # fp32 atomic summation order only
+    assert np.allclose(full[0], full[1] + full[2], rtol=1e-5, atol=1e-6)
+    C_ = make_renderer(api, name, W, H, ns_aa=ns, max_ray_depth=m, seed=6)
+    C_.render()
+    assert not np.allclose(C_.framebuffer(0), full[0], rtol=1e-3, atol=1e-4)
+    assert 0.2 < full[0].mean() < 0.8
+
+
+def test_config2_full_size_runs_and_tonemaps(api):
+    """configs[1]: CBspheres 480x360, 128 spp, m=5 (mirror + glass)."""
+    R = make_renderer(api, "CBspheres", 480, 360, ns_aa=128, max_ray_depth=5, seed=2)
+    R.render()
+    img = R.framebuffer(0)
+    assert np.isfinite(img).all() and 0.2 < img.mean() < 0.8
+    png = R.tonemap(0)
+    assert png.shape == (360, 480, 4) and png[..., 3].min() == 255
+    # toColor: exposure sqrt(2), gamma 2.2, truncation; PNG rows are top-down
+    exp = np.clip(np.power(np.maximum(img[::-1], 0) * np.float32(np.sqrt(2)), 1 / 2.2), 0, 1) * 255
+    assert np.mean(np.abs(png[..., :3].astype(np.int32) - exp.astype(np.int32)) <= 1) > 0.999
+
+
+def test_roulette_is_unbiased(api):
+    name, W, H, m = "CBspheres_lambertian", 48, 36, 6
+    a = make_renderer(api, name, W, H, ns_aa=1024, max_ray_depth=m, seed=3); a.render()
+    b = make_renderer(api, name, W, H, ns_aa=1024, max_ray_depth=m, seed=4, roulette=True); b.render()
+    ia, ib = a.framebuffer(0), b.framebuffer(0)
+    assert abs(ia.mean() - ib.mean()) <= 1e-2 * ia.mean()
+    assert relmse(ib, ia) <= 5e-3
+    assert b.stats()["rays_closest"] < a.stats()["rays_closest"]
+
+
+# --------------------------------------------------------------------------------- error behaviour
+def test_error_paths(api):
+    import ctypes as C
+    R = api.Renderer(0)
+    with pytest.raises(api.BdptError, match="no scene"):
+        R.render()
+    sc = load_scene("CBempty")
+    bad = sc.lights.copy(); bad["type"] = 7
+    from bdpt import flatscene as fs
+    with pytest.raises(api.BdptError, match="light type"):
+        R.set_scene(fs.FlatScene(sc.camera, sc.materials, bad, sc.prims))
+    badp = sc.prims.copy(); badp["material"][0] = 99
+    with pytest.raises(api.BdptError, match="material"):
+        R.set_scene(fs.FlatScene(sc.camera, sc.materials, sc.lights, badp))
+    R.set_scene(sc)
+    with pytest.raises(api.BdptError, match="frame"):
+        R.render()
+    R.set_frame_size(32, 24)
+    R.ns_aa = 0
+    with pytest.raises(api.BdptError, match="parameters"):
+        R.render()
+    # m = 0 behaves as m = 1: the walk stores a vertex before testing the depth (bidirection.cpp:82-86)
+    R.ns_aa, R.max_ray_depth = 2, 0
+    R.render()
+    a = R.framebuffer(0)
+    R.clear(); R.max_ray_depth = 1; R.render()
+    assert a.max() > 0 and np.allclose(a, R.framebuffer(0), rtol=1e-5, atol=1e-6)
