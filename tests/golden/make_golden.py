@@ -57,10 +57,12 @@ def ray_batch(sc, rng, n):
     a = rng.uniform(lo, hi, (n - 2 * k, 3)); b = rng.uniform(lo, hi, (n - 2 * k, 3))
     dist = np.linalg.norm(b - a, axis=1, keepdims=True)
     r3 = np.concatenate([a, (b - a) / dist, np.full_like(dist, float(np.float32(1e-5))), dist - float(np.float32(1e-5))], 1)
-    return np.concatenate([r1, r2, r3], 0)
+    # every number exactly representable in fp32, so the fp64 reference and the fp32 CUDA path are given the SAME ray
+    return np.concatenate([r1, r2, r3], 0).astype(np.float32).astype(np.float64)
 
 
 def main():
+    only = sys.argv[1] if len(sys.argv) > 1 else "all"
     assert O.have_ref(), "build the reference first: make -C oracle ref"
     os.makedirs(os.path.join(OUT, "scenes"), exist_ok=True)
     for name, (W, H, ns, m) in SCENES.items():
@@ -77,22 +79,29 @@ def main():
         M = 600
         bq = np.zeros((M, 7)); bq[:, 0] = rng.integers(0, len(sc.materials), M)
         bq[:, 1:4] = unit(rng.normal(size=(M, 3))); bq[:, 4:7] = unit(rng.normal(size=(M, 3)))
+        bq = bq.astype(np.float32).astype(np.float64)
         bout = O.ref_batch("bsdf", dae, bq, 7, 8)
         lq = np.zeros((M, 7)); lq[:, 0] = rng.integers(0, len(sc.lights), M)
         lq[:, 1:4] = rng.uniform([-1, 0, -1], [1, 1.5, 1], (M, 3))
         on = sc.lights["position"][lq[: M // 2, 0].astype(int)]
         lq[: M // 2, 2] = on[:, 1]  # on the light's plane (scenes are Y-up, lights face -Y)
         lq[:, 4:7] = unit(rng.normal(size=(M, 3)))
+        lq = lq.astype(np.float32).astype(np.float64)
         lout = O.ref_batch("light", dae, lq, 7, 6)
         cq = np.zeros((M, 5)); cq[:, 0:2] = rng.uniform(0, 1, (M, 2)); cq[:, 2:5] = rng.uniform([-1, 0, -1], [1, 1.5, 1], (M, 3))
+        cq = cq.astype(np.float32).astype(np.float64)
         cout = O.ref_batch("camera", dae, cq, 5, 11, extra=(480, 360))
         np.savez_compressed(os.path.join(OUT, name + ".units.npz"), rays=rays, hits=hits, bsdf_in=bq, bsdf_out=bout,
                             light_in=lq, light_out=lout, cam_in=cq, cam_out=cout, cam_wh=np.array([480, 360]))
+        if only == "units":
+            continue
         s, e, l, info = O.ref_render(dae, W, H, ns, m, threads=1)
         np.savez_compressed(os.path.join(OUT, name + ".render.npz"), sum=s, eye=e, light=l,
                             params=np.array([W, H, ns, m]), rays=np.array([info["rays"]]))
         print(name, "prims", sc.n_prims, "render rays", info["rays"])
 
+    if only == "units":
+        return
     # converged reference renders (the reference's own binary, all host threads): the level-3 pin
     for name, (W, H, ns, m) in {"CBspheres_lambertian": (64, 48, 1024, 5), "CBspheres": (64, 48, 1024, 5),
                                 "CBgems": (64, 48, 1024, 5)}.items():
