@@ -51,11 +51,20 @@ struct BdptContext {
   unsigned int* qctr = nullptr;
   unsigned long long* d_stats = nullptr;
   unsigned int* h_qctr = nullptr;  // pinned
+  // wavefront walk (sched == 2)
+  WfBuf wf{}; size_t wf_cap = 0; int wf_cap_m = -1;
 
   // stats
   BdptStats stats{};
   std::vector<cudaEvent_t> ev;
   int sm_count = 148;
+  // walk scheduler: 0 = one subpath per lane, 1 = persistent per-lane state machine, 2 = per-bounce wavefront
+  // (measured slower: its state round-trips cost more HBM time than the divergence it removes); -1 = choose by
+  // BVH size at upload (tiny trees have no traversal divergence to hide).  Override: BDPT_SCHED.
+  int sched = -1, sched_req = -1;
+  int variant = 1;      // scheduling-threshold variant of k_walk_pt (BDPT_VARIANT, tuning only)
+  int connect_minb = 6; // __launch_bounds__ min blocks of k_connect (BDPT_CONNECT_MINB, tuning only)
+  int walk_ctas = 4, shadow_ctas = 8;  // resident CTAs per SM of the persistent kernels
 };
 
 namespace {
@@ -146,6 +155,18 @@ int ensure_batch_storage(BdptContext* ctx, size_t B, int m, size_t qcap) {
     CK(cudaMalloc(&ctx->q2, qcap * sizeof(float4)));
     ctx->cap_q = qcap;
   }
+  if (ctx->sched == 2 && (2 * B > ctx->wf_cap || m > ctx->wf_cap_m)) {
+    WfBuf& F = ctx->wf;
+    dfree(F.r0); dfree(F.r1); dfree(F.h); dfree(F.s0); dfree(F.s1); dfree(F.s2); dfree(F.s3); dfree(F.s4);
+    dfree(F.queue_a); dfree(F.queue_b); dfree(F.ctr);
+    size_t n = std::max(2 * B, ctx->wf_cap); int nm = std::max(m, ctx->wf_cap_m);
+    float4** planes[8] = {&F.r0, &F.r1, &F.h, &F.s0, &F.s1, &F.s2, &F.s3, &F.s4};
+    for (auto pp : planes) CK(cudaMalloc(pp, n * sizeof(float4)));
+    CK(cudaMalloc(&F.queue_a, n * sizeof(unsigned int)));
+    CK(cudaMalloc(&F.queue_b, n * sizeof(unsigned int)));
+    CK(cudaMalloc(&F.ctr, 4 * (size_t)(nm + 3) * sizeof(unsigned int)));
+    ctx->wf_cap = n; ctx->wf_cap_m = nm;
+  }
   if (!ctx->qctr) {
     CK(cudaMalloc(&ctx->qctr, 4 * sizeof(unsigned int)));
     CK(cudaMalloc(&ctx->d_stats, 4 * sizeof(unsigned long long)));
@@ -181,12 +202,45 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
   CK(cudaMemsetAsync(ctx->qctr, 0, 4 * sizeof(unsigned int), ctx->stream));
   const int threads = 128;
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 0), ctx->stream);
-  k_walk<<<(2 * J.B + threads - 1) / threads, threads, 0, ctx->stream>>>(J);
+  if (ctx->sched == 2) {
+    // wavefront walk: generate, then per bounce trace + shade (2m + 1 launches)
+    WfBuf F = ctx->wf;
+    unsigned int* ctr0 = F.ctr;
+    CK(cudaMemsetAsync(ctr0, 0, 4 * (size_t)(J.m + 3) * sizeof(unsigned int), ctx->stream));
+    const unsigned n2 = 2u * (unsigned)J.B;
+    k_wf_gen<<<(n2 + threads - 1) / threads, threads, 0, ctx->stream>>>(J, F);
+    for (int b = 0; b < J.m; b++) {
+      F.ctr = ctr0 + 4 * b;
+      k_wf_trace<<<ctx->sm_count * ctx->shadow_ctas, threads, 0, ctx->stream>>>(J, F, b == 0 ? n2 : 0u);
+      k_wf_shade<<<(n2 + threads - 1) / threads, threads, 0, ctx->stream>>>(J, F, b == 0 ? n2 : 0u);
+      std::swap(F.queue_a, F.queue_b);   // this bounce's survivors are the next bounce's input
+    }
+    ctx->stats.kernel_launches += 2 * J.m;
+  } else if (ctx->sched) {
+    const int g = ctx->sm_count * ctx->walk_ctas;
+    switch (ctx->variant) {
+      case 1: k_walk_pt<16, 8><<<g, threads, 0, ctx->stream>>>(J); break;
+      case 2: k_walk_pt<20, 8><<<g, threads, 0, ctx->stream>>>(J); break;
+      case 3: k_walk_pt<12, 4><<<g, threads, 0, ctx->stream>>>(J); break;
+      case 4: k_walk_pt<16, 16><<<g, threads, 0, ctx->stream>>>(J); break;
+      case 5: k_walk_pt<8, 8><<<g, threads, 0, ctx->stream>>>(J); break;
+      default: k_walk_pt<12, 8><<<g, threads, 0, ctx->stream>>>(J); break;
+    }
+  }
+  else k_walk<<<(2 * J.B + threads - 1) / threads, threads, 0, ctx->stream>>>(J);
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 1), ctx->stream);
-  dim3 grid((J.B + threads - 1) / threads, J.m + 1);
-  k_connect<TRACE><<<grid, threads, 0, ctx->stream>>>(J);
+  const unsigned cgrid = (unsigned)((J.B + threads - 1) / threads) * (unsigned)(J.m + 1);
+  switch (TRACE ? 0 : ctx->connect_minb) {
+    case 4: k_connect<TRACE, 4><<<cgrid, threads, 0, ctx->stream>>>(J); break;
+    case 5: k_connect<TRACE, 5><<<cgrid, threads, 0, ctx->stream>>>(J); break;
+    case 6: k_connect<TRACE, 6><<<cgrid, threads, 0, ctx->stream>>>(J); break;
+    case 8: k_connect<TRACE, 8><<<cgrid, threads, 0, ctx->stream>>>(J); break;
+    case 10: k_connect<TRACE, 10><<<cgrid, threads, 0, ctx->stream>>>(J); break;
+    default: k_connect<TRACE, 3><<<cgrid, threads, 0, ctx->stream>>>(J); break;
+  }
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 2), ctx->stream);
-  k_shadow<<<ctx->sm_count * 8, threads, 0, ctx->stream>>>(J);
+  if (ctx->sched) k_shadow_pt<<<ctx->sm_count * ctx->shadow_ctas, threads, 0, ctx->stream>>>(J);
+  else k_shadow<<<ctx->sm_count * 8, threads, 0, ctx->stream>>>(J);
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 3), ctx->stream);
   ctx->stats.kernel_launches += 3;
   CK(cudaGetLastError());
@@ -243,6 +297,12 @@ int bdpt_create(int device, BdptContext** out) {
   if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return BDPT_ERR_CUDA; }
   ctx->own_stream = true;
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (const char* e = getenv("BDPT_SCHED")) ctx->sched_req = atoi(e);
+  ctx->sched = ctx->sched_req >= 0 ? ctx->sched_req : 1;
+  if (const char* e = getenv("BDPT_CONNECT_MINB")) ctx->connect_minb = atoi(e);
+  if (const char* e = getenv("BDPT_VARIANT")) ctx->variant = atoi(e);
+  if (const char* e = getenv("BDPT_WALK_CTAS")) ctx->walk_ctas = std::max(1, atoi(e));
+  if (const char* e = getenv("BDPT_SHADOW_CTAS")) ctx->shadow_ctas = std::max(1, atoi(e));
   *out = ctx;
   return BDPT_OK;
 }
@@ -255,6 +315,7 @@ void bdpt_destroy(BdptContext* ctx) {
   dfree(ctx->acc_eye); dfree(ctx->acc_light); dfree(ctx->resolve_tmp); dfree(ctx->rgba_tmp);
   dfree(ctx->v0); dfree(ctx->v1); dfree(ctx->v2); dfree(ctx->v3); dfree(ctx->counts);
   dfree(ctx->q0); dfree(ctx->q1); dfree(ctx->q2); dfree(ctx->qctr); dfree(ctx->d_stats);
+  { WfBuf& F = ctx->wf; dfree(F.r0); dfree(F.r1); dfree(F.h); dfree(F.s0); dfree(F.s1); dfree(F.s2); dfree(F.s3); dfree(F.s4); dfree(F.queue_a); dfree(F.queue_b); dfree(F.ctr); }
   if (ctx->h_qctr) cudaFreeHost(ctx->h_qctr);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -364,6 +425,7 @@ int bdpt_upload_scene(BdptContext* ctx, const BdptCamera* camera, const BdptMate
   ctx->sc.n_lights = (int)n_lights; ctx->sc.n_materials = (int)n_materials;
   ctx->sc.n_nodes = (int)(bvh.nodes.size() / 20); ctx->sc.n_prims = (int)n_prims;
   ctx->bvh_nodes = (uint32_t)(bvh.nodes.size() / 20); ctx->bvh_depth = bvh.max_depth;
+  ctx->sched = ctx->sched_req >= 0 ? ctx->sched_req : (ctx->bvh_nodes > 8 ? 1 : 0);
   ctx->cam_base = *camera;
   ctx->have_scene = true;
   if (ctx->W > 0) make_dcamera(ctx->cam_base, ctx->W, ctx->H, &ctx->cam);
@@ -441,6 +503,7 @@ int bdpt_render(BdptContext* ctx, const BdptRenderParams* p) {
   CK(cudaEventRecord(e0, ctx->stream));
   for (unsigned long long b = 0; b < n_batches; b++) {
     J.g0 = b * B;
+    J.k0 = (unsigned int)(J.g0 / (unsigned long long)npix_pad); J.p0 = (unsigned int)(J.g0 % (unsigned long long)npix_pad);
     rc = run_batch<false>(ctx, J, b < (unsigned long long)timed ? 2 + 4 * (long)b : -1);
     if (rc) return rc;
   }

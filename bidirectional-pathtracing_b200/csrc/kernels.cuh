@@ -46,6 +46,7 @@ struct Job {
   double* dbg;                // trace of one sample (bdpt_trace_sample) or null
   unsigned long long seed;
   unsigned long long g0;      // first job-sample index of this batch
+  unsigned int k0, p0;        // g0 = k0 * npix_pad + p0 (split on the host: no 64-bit division on the device)
   unsigned long long g_end;   // one past the last job-sample index of the job
   int B;                      // samples in this batch
   int m;                      // max_ray_depth
@@ -61,8 +62,9 @@ struct Job {
 __device__ inline bool decode_sample(const Job& J, unsigned long long g, int* x, int* y, int* sample) {
   if (g >= J.g_end) return false;
   if (J.single_x >= 0) { *x = J.single_x; *y = J.single_y; *sample = J.first_sample + (int)g; return true; }
-  unsigned long long k = g / (unsigned long long)J.npix_pad;
-  int p = (int)(g - k * (unsigned long long)J.npix_pad);
+  unsigned int q = J.p0 + (unsigned int)(g - J.g0);   // < npix_pad + B < 2^32
+  unsigned int k = J.k0 + q / (unsigned int)J.npix_pad;
+  int p = (int)(q % (unsigned int)J.npix_pad);
   int tile = p >> 5, w = p & 31;
   int tx = tile % J.tiles_x, ty = tile / J.tiles_x;
   *x = tx * 8 + (w & 7);
@@ -205,10 +207,28 @@ __device__ inline void push_shadow(const Job& J, bool push, f3 o, f3 dir, float 
   J.q2[idx] = make_float4(ill.x, ill.y, ill.z, 0.f);
 }
 
-template <bool TRACE>
-__global__ void __launch_bounds__(128) k_connect(const Job J) {
-  const int si = blockIdx.x * blockDim.x + threadIdx.x;
-  const int t = blockIdx.y + 1;
+struct VRaw { float4 a, b, c, e; };
+__device__ inline VRaw load_raw(const Job& J, int kind, int j, int si) {
+  size_t s = VSLOT(J, kind, j, si);
+  VRaw r; r.a = J.v0[s]; r.b = J.v1[s]; r.c = J.v2[s]; r.e = J.v3[s];
+  return r;
+}
+__device__ inline Vtx unpack(const VRaw& r) {
+  Vtx v;
+  v.pos = mk3(r.a.x, r.a.y, r.a.z); v.mat = __float_as_int(r.a.w);
+  v.n = mk3(r.b.x, r.b.y, r.b.z); v.D = r.b.w;
+  v.alpha = mk3(r.c.x, r.c.y, r.c.z); v.S = r.c.w;
+  v.wo = mk3(r.e.x, r.e.y, r.e.z); v.q = r.e.w;
+  return v;
+}
+
+// Grid: 1-D, the (m+1) values of t of one group of 128 samples are consecutive blocks, so the light
+// vertices those blocks share are fetched from DRAM once and found in L2 by the other m.  Inside the
+// s loop nothing is prefetched: holding a second vertex costs 33 registers and an occupancy step.
+template <bool TRACE, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_connect(const Job J) {
+  const int t = (int)(blockIdx.x % (unsigned)(J.m + 1)) + 1;
+  const int si = (int)(blockIdx.x / (unsigned)(J.m + 1)) * blockDim.x + threadIdx.x;
   if (si >= J.B) return;
   const int nE = J.counts[si];
   const int nL = J.counts[J.B + si];
@@ -334,7 +354,7 @@ __global__ void __launch_bounds__(128) k_connect(const Job J) {
         } else {
           // s == 1: the chain is evaluated at the ORIGINAL light-subpath origin
           size_t s1 = VSLOT(J, 1, 1, si);
-          float4 a = J.v0[s1], b = J.v1[s1];
+          const float4 a = J.v0[s1], b = J.v1[s1];   // light_path[1]
           f3 wv = mk3(a.x, a.y, a.z) - ve_pos;
           float d2 = dot(wv, wv);
           f3 wd = wv * rsqrtf(d2);
@@ -398,6 +418,324 @@ __global__ void __launch_bounds__(128) k_shadow(const Job J) {
   }
   unsigned int tot = __reduce_add_sync(0xffffffffu, traced);
   if (lane == 0 && tot) atomicAdd(J.stats + 1, (unsigned long long)tot);
+}
+
+// ------------------------------------------------------------------- persistent (scheduled) kernels
+// The two traversal kernels above give every lane one ray (or one subpath) and wait for the
+// slowest lane of the warp: ncu shows 6.6 (k_walk) and 9.0 (k_shadow) active lanes per instruction
+// (profiles/r01_*).  The persistent forms keep a lane busy: warps claim work in chunks with one
+// atomic per chunk, hand indices to idle lanes with ballot + popc prefix, and run the resumable
+// traversal (Trav::step) as a per-lane state machine; lanes refill the moment their ray ends.
+struct WarpFetch {   // warp-uniform
+  unsigned next, end;
+  bool exhausted;
+};
+
+#define BDPT_NONE 0xffffffffu
+
+// All 32 lanes call this.  Lanes with want == true receive distinct work indices (or BDPT_NONE).
+__device__ inline unsigned warp_fetch(unsigned* cursor, unsigned total, unsigned chunk, bool want, WarpFetch& wf) {
+  const unsigned mask = __ballot_sync(0xffffffffu, want);
+  if (mask == 0u || wf.exhausted) return BDPT_NONE;
+  const int lane = threadIdx.x & 31;
+  if (wf.next >= wf.end) {
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(cursor, chunk);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= total) { wf.exhausted = true; return BDPT_NONE; }
+    wf.next = base;
+    wf.end = min(base + chunk, total);
+  }
+  const unsigned my = wf.next + __popc(mask & ((1u << lane) - 1u));
+  const bool got = want && my < wf.end;
+  wf.next = min(wf.next + (unsigned)__popc(mask), wf.end);
+  return got ? my : BDPT_NONE;
+}
+
+__global__ void __launch_bounds__(128) k_shadow_pt(const Job J) {
+  const unsigned n = min(J.qctr[0], J.qcap);
+  Trav T;
+  uint2 stack[BDPT_STACK];
+  bool active = false;
+  unsigned idx = 0, traced = 0;
+  WarpFetch wf; wf.next = 0; wf.end = 0; wf.exhausted = false;
+#pragma unroll 1
+  for (;;) {
+    const unsigned idle = __ballot_sync(0xffffffffu, !active);
+    if (!wf.exhausted && (__popc(idle) >= 4 || idle == 0xffffffffu)) {
+      unsigned my = warp_fetch(J.qctr + 1, n, 256u, !active, wf);
+      if (my != BDPT_NONE) {
+        float4 a = J.q0[my], b = J.q1[my];
+        T.begin(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), BDPT_EPS_F, a.w);
+        idx = my; active = true;
+      }
+    }
+    if (__ballot_sync(0xffffffffu, active) == 0u) {
+      if (wf.exhausted) break;
+      continue;
+    }
+    if (active && T.step<true>(J.sc, stack)) {
+      traced++;
+      active = false;
+      if (T.hit.leaf < 0) {
+        float4 b = J.q1[idx], c = J.q2[idx];
+        unsigned int tg = __float_as_uint(b.w);
+        float* px = ((tg & 0x80000000u) ? J.acc_light : J.acc_eye) + 3 * (size_t)(tg & 0x7fffffffu);
+        atomicAdd(px + 0, c.x); atomicAdd(px + 1, c.y); atomicAdd(px + 2, c.z);
+      }
+    }
+  }
+  unsigned int tot = __reduce_add_sync(0xffffffffu, traced);
+  if ((threadIdx.x & 31) == 0 && tot) atomicAdd(J.stats + 1, (unsigned long long)tot);
+}
+
+// Per-lane subpath state of the persistent walk.
+struct WalkState {
+  Rng rng;
+  f3 prev_n, alpha, prev_f;
+  float prev_pdf, pdfeval_prev, D_prev, S_prev;
+  int kind, si, j, nv;
+  bool delta_prev;
+};
+
+// New subpath: pinhole ray (raytrace_pixel, bidirection.cpp:517-524) or light emission
+// (sample_light_ray, :105-118).  Returns false if the index maps to no pixel.
+__device__ inline bool walk_begin(const Job& J, unsigned i, WalkState& W, Trav& T) {
+  W.kind = i >= (unsigned)J.B ? 1 : 0;
+  W.si = (int)i - W.kind * J.B;
+  int x, y, sample;
+  if (!decode_sample(J, J.g0 + (unsigned long long)W.si, &x, &y, &sample)) { J.counts[i] = 0; return false; }
+  W.rng.begin(J.seed, (unsigned long long)y * (unsigned long long)J.cam.W + (unsigned long long)x,
+              (unsigned long long)sample, (uint32_t)W.kind);
+  W.prev_f = mk3(1.f); W.delta_prev = false; W.nv = 1; W.j = 2;
+  f3 o, d;
+  if (W.kind == 0) {
+    float sx = W.rng.uniform(), sy = W.rng.uniform();
+    camera_generate_ray(J.cam, ((float)x + sx) / (float)J.cam.W, ((float)y + sy) / (float)J.cam.H, &o, &d);
+    W.prev_n = d; W.alpha = mk3(1.f); W.prev_pdf = 1.f;
+    W.pdfeval_prev = 1.f; W.D_prev = 1.f; W.S_prev = 0.f;
+    T.begin(o, d, J.cam.nclip, J.cam.fclip);
+  } else {
+    int li = W.rng.pick(J.sc.n_lights);
+    Light L = load_light(J.sc, li);
+    float pA, pdir; f3 nl;
+    f3 Le = light_sample_Le(L, W.rng, &o, &d, &pA, &pdir, &nl);
+    pA /= (float)J.sc.n_lights;
+    W.prev_n = nl; W.alpha = Le * (1.0f / pA); W.prev_pdf = pdir;
+    W.pdfeval_prev = pdir; W.D_prev = pA; W.S_prev = 1.f;
+    size_t s1 = VSLOT(J, 1, 1, W.si);
+    J.v0[s1] = make_float4(o.x, o.y, o.z, __int_as_float(-1));
+    J.v1[s1] = make_float4(nl.x, nl.y, nl.z, pA);
+    J.v2[s1] = make_float4(W.alpha.x, W.alpha.y, W.alpha.z, 1.f);
+    J.v3[s1] = make_float4(pdir, 0.f, 0.f, 1.f);
+    T.begin(o, d, BDPT_EPS_F, INFINITY);
+  }
+  return true;
+}
+
+// The traversal of the current ray finished: store the vertex (if any) and sample the next ray
+// (body of the while loop of prepare_bidirectional_subpath, bidirection.cpp:44-101).
+// Returns true if the subpath continues (T holds the next ray), false if it ended.
+__device__ inline bool walk_shade(const Job& J, WalkState& W, Trav& T) {
+  const DScene& sc = J.sc;
+  if (T.hit.leaf < 0) return false;
+  const f3 o = T.o, d = T.d;
+  f3 n, hit_p; int prim, mat;
+  finish_hit(sc, T.hit, o, d, &n, &prim, &mat, &hit_p);
+  const float t = T.hit.t;
+  const Frame fr = make_frame(n);
+  const f3 w_out = fr.to_local(-d);
+  const Mat M = load_mat(sc, mat);
+  f3 wi; float pdf;
+  const f3 f = bsdf_sample_f(M, w_out, &wi, &pdf, W.rng);
+  const f3 wi_world = normalized(fr.to_world(wi));
+
+  const float cos_prev = fabsf(dot(W.prev_n, d));
+  const float g = cos_prev * fabsf(dot(n, d)) / (t * t);
+  W.alpha = W.alpha * W.prev_f * (cos_prev / W.prev_pdf);
+
+  float p_keep = 1.f;
+  if (J.roulette && W.j > 2) p_keep = fminf(1.f, norm(f) / pdf);
+
+  const bool delta_j = type_is_delta(M.type);
+  const float D_j = (W.kind == 0 && W.j == 2) ? 1.f : W.pdfeval_prev * g;
+  const f3 zero = mk3(0.f);
+  const float D_rev = bsdf_pdf(M, zero, w_out) * p_keep * g;
+  float S_j = (delta_j || W.delta_prev) ? 0.f : 1.f;
+  if (W.S_prev > 0.f) { float R = D_rev / W.D_prev; S_j += R * R * W.S_prev; }
+  S_j = clampS(S_j);
+
+  size_t sl = VSLOT(J, W.kind, W.j, W.si);
+  J.v0[sl] = make_float4(hit_p.x, hit_p.y, hit_p.z, __int_as_float(mat));
+  J.v1[sl] = make_float4(n.x, n.y, n.z, D_j);
+  J.v2[sl] = make_float4(W.alpha.x, W.alpha.y, W.alpha.z, S_j);
+  J.v3[sl] = make_float4(-d.x, -d.y, -d.z, p_keep);
+  W.nv = W.j;
+  if (W.j >= J.m + 1) return false;
+  if (J.roulette && !(W.rng.uniform() < p_keep)) return false;
+  if (is_zero(f)) return false;
+
+  W.pdfeval_prev = bsdf_pdf(M, zero, wi) * p_keep;
+  W.prev_f = f; W.prev_n = n; W.prev_pdf = pdf * p_keep;
+  W.D_prev = D_j; W.S_prev = S_j; W.delta_prev = delta_j;
+  W.j++;
+  T.begin(hit_p, wi_world, BDPT_EPS_F, INFINITY);
+  return true;
+}
+
+// phase: 0 = empty (wants a subpath), 1 = traversing, 2 = traversal finished (wants shading)
+template <int SHADE_THRESHOLD, int FETCH_THRESHOLD>
+__global__ void __launch_bounds__(128) k_walk_pt(const Job J) {
+  Trav T;
+  uint2 stack[BDPT_STACK];
+  WalkState W;
+  int phase = 0;
+  unsigned nrays = 0;
+  WarpFetch wf; wf.next = 0; wf.end = 0; wf.exhausted = false;
+  const unsigned total = 2u * (unsigned)J.B;
+#pragma unroll 1
+  for (;;) {
+    const unsigned trav = __ballot_sync(0xffffffffu, phase == 1);
+    const unsigned shade = __ballot_sync(0xffffffffu, phase == 2);
+    // shading waits until enough lanes want it (or nothing else can run) ...
+    if (shade != 0u && (trav == 0u || __popc(shade) >= SHADE_THRESHOLD)) {
+      if (phase == 2) {
+        if (walk_shade(J, W, T)) phase = 1;
+        else { J.counts[W.kind * J.B + W.si] = W.nv; phase = 0; }
+      }
+    }
+    // ... and so does starting new subpaths
+    const unsigned empty = __ballot_sync(0xffffffffu, phase == 0);
+    if (empty != 0u && !wf.exhausted && (__popc(empty) >= FETCH_THRESHOLD || __ballot_sync(0xffffffffu, phase == 1) == 0u)) {
+      unsigned my = warp_fetch(J.qctr + 3, total, 128u, phase == 0, wf);
+      if (my != BDPT_NONE && walk_begin(J, my, W, T)) phase = 1;
+    }
+    if (__ballot_sync(0xffffffffu, phase != 0) == 0u && wf.exhausted) break;
+    if (phase == 1) {
+      if (T.step<false>(J.sc, stack)) { phase = 2; nrays++; }
+    }
+  }
+  unsigned int tot = __reduce_add_sync(0xffffffffu, nrays);
+  if ((threadIdx.x & 31) == 0 && tot) atomicAdd(J.stats + 0, (unsigned long long)tot);
+}
+
+// ------------------------------------------------------------------- wavefront walk (per bounce)
+// The walk split at the ray boundary: k_wf_gen writes every subpath's first ray; then, per bounce,
+// k_wf_trace (persistent, dynamic fetch, pure closest-hit traversal: few registers, small code)
+// fills a hit record per live subpath and k_wf_shade (one thread per live subpath, full warps)
+// stores the vertex, samples the BSDF and compacts the survivors into the next bounce's queue
+// with ballot + prefix.  Subpath state lives in SoA planes indexed by subpath id:
+//   r0 = {o, tmin}  r1 = {d, tmax}  h = {t, leaf, b1, b2}
+//   s0 = rng {state, inc}  s1 = {alpha, prev_pdf}  s2 = {prev_f, pdfeval_prev}
+//   s3 = {prev_n, D_prev}  s4 = {S_prev, j | delta_prev << 8, nv, -}
+struct WfBuf {
+  float4 *r0, *r1, *h, *s0, *s1, *s2, *s3, *s4;
+  unsigned int *queue_a, *queue_b;   // subpath ids alive at this / the next bounce
+  unsigned int* ctr;                 // this bounce: [0] n_in  [1] trace cursor; [4] = n_in of the next bounce
+};
+
+__device__ inline void wf_store_state(const WfBuf& F, unsigned i, const WalkState& W) {
+  ulonglong2 r; r.x = W.rng.state; r.y = W.rng.inc;
+  *reinterpret_cast<ulonglong2*>(F.s0 + i) = r;
+  F.s1[i] = make_float4(W.alpha.x, W.alpha.y, W.alpha.z, W.prev_pdf);
+  F.s2[i] = make_float4(W.prev_f.x, W.prev_f.y, W.prev_f.z, W.pdfeval_prev);
+  F.s3[i] = make_float4(W.prev_n.x, W.prev_n.y, W.prev_n.z, W.D_prev);
+  F.s4[i] = make_float4(W.S_prev, __int_as_float(W.j | (W.delta_prev ? 256 : 0)), __int_as_float(W.nv), 0.f);
+}
+
+__device__ inline void wf_load_state(const WfBuf& F, unsigned i, int B, WalkState& W) {
+  ulonglong2 r = *reinterpret_cast<const ulonglong2*>(F.s0 + i);
+  W.rng.state = r.x; W.rng.inc = r.y;
+  float4 a = F.s1[i], b = F.s2[i], c = F.s3[i], d = F.s4[i];
+  W.alpha = mk3(a.x, a.y, a.z); W.prev_pdf = a.w;
+  W.prev_f = mk3(b.x, b.y, b.z); W.pdfeval_prev = b.w;
+  W.prev_n = mk3(c.x, c.y, c.z); W.D_prev = c.w;
+  W.S_prev = d.x;
+  int jj = __float_as_int(d.y);
+  W.j = jj & 255; W.delta_prev = (jj & 256) != 0; W.nv = __float_as_int(d.z);
+  W.kind = i >= (unsigned)B ? 1 : 0;
+  W.si = (int)i - W.kind * B;
+}
+
+__global__ void __launch_bounds__(128) k_wf_gen(const Job J, const WfBuf F) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2u * (unsigned)J.B) return;
+  WalkState W; Trav T;
+  bool ok = walk_begin(J, i, W, T);
+  // first bounce: the queue is the identity; dead (padding) lanes get a ray that cannot hit
+  F.r0[i] = make_float4(T.o.x, T.o.y, T.o.z, ok ? T.tmin : 1.f);
+  F.r1[i] = make_float4(T.d.x, T.d.y, T.d.z, ok ? T.hit.t : 0.f);
+  if (ok) wf_store_state(F, i, W);
+  else F.s4[i] = make_float4(0.f, __int_as_float(0), __int_as_float(0), 0.f);
+}
+
+// n_in = F.ctr[0] (or `fixed_n` for the first bounce, where the queue is the identity)
+__global__ void __launch_bounds__(128) k_wf_trace(const Job J, const WfBuf F, const unsigned fixed_n) {
+  const unsigned n = fixed_n ? fixed_n : F.ctr[0];
+  Trav T;
+  uint2 stack[BDPT_STACK];
+  bool active = false;
+  unsigned id = 0, traced = 0;
+  WarpFetch wf; wf.next = 0; wf.end = 0; wf.exhausted = false;
+#pragma unroll 1
+  for (;;) {
+    const unsigned idle = __ballot_sync(0xffffffffu, !active);
+    if (!wf.exhausted && (__popc(idle) >= 4 || idle == 0xffffffffu)) {
+      unsigned my = warp_fetch(F.ctr + 1, n, 256u, !active, wf);
+      if (my != BDPT_NONE) {
+        id = fixed_n ? my : F.queue_a[my];
+        float4 a = F.r0[id], b = F.r1[id];
+        T.begin(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), a.w, b.w);
+        active = true;
+      }
+    }
+    if (__ballot_sync(0xffffffffu, active) == 0u) {
+      if (wf.exhausted) break;
+      continue;
+    }
+    if (active && T.step<false>(J.sc, stack)) {
+      traced++;
+      active = false;
+      F.h[id] = make_float4(T.hit.t, __int_as_float(T.hit.leaf), T.hit.b1, T.hit.b2);
+    }
+  }
+  unsigned int tot = __reduce_add_sync(0xffffffffu, traced);
+  if ((threadIdx.x & 31) == 0 && tot) atomicAdd(J.stats + 0, (unsigned long long)tot);
+}
+
+__global__ void __launch_bounds__(128) k_wf_shade(const Job J, const WfBuf F, const unsigned fixed_n) {
+  const unsigned n = fixed_n ? fixed_n : F.ctr[0];
+  const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+  bool cont = false;
+  unsigned id = 0;
+  if (q < n) {
+    id = fixed_n ? q : F.queue_a[q];
+    WalkState W;
+    wf_load_state(F, id, J.B, W);
+    if (W.j != 0) {   // j == 0 marks a padding lane of the first bounce
+      Trav T;
+      float4 a = F.r0[id], b = F.r1[id], h = F.h[id];
+      T.o = mk3(a.x, a.y, a.z); T.d = mk3(b.x, b.y, b.z);
+      T.hit.t = h.x; T.hit.leaf = __float_as_int(h.y); T.hit.b1 = h.z; T.hit.b2 = h.w;
+      cont = walk_shade(J, W, T);
+      if (cont) {
+        F.r0[id] = make_float4(T.o.x, T.o.y, T.o.z, T.tmin);
+        F.r1[id] = make_float4(T.d.x, T.d.y, T.d.z, T.hit.t);
+        wf_store_state(F, id, W);
+      } else {
+        J.counts[W.kind * J.B + W.si] = W.nv;
+      }
+    }
+  }
+  // compact the survivors into the next bounce's queue
+  const unsigned mask = __ballot_sync(0xffffffffu, cont);
+  if (mask) {
+    const int lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(F.ctr + 4, (unsigned)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (cont) F.queue_b[base + __popc(mask & ((1u << lane) - 1u))] = id;
+  }
 }
 
 // ------------------------------------------------------------------------------ test-hook kernels

@@ -61,23 +61,34 @@ __device__ inline bool intersect_prim(const float4* __restrict__ prims, int k, f
   return false;
 }
 
-template <bool ANY_HIT>
-__device__ inline Hit traverse(const DScene& sc, f3 o, f3 d, float tmin, float tmax) {
+// Resumable traversal state: begin() then step() until it returns true.  One step = pop the nearest
+// pending internal child, test its 8 children, test the primitives of the leaf children that were
+// hit.  Being resumable is what lets the persistent kernels refill a lane the moment its ray ends
+// instead of idling until the slowest ray of the warp is done.
+struct Trav {
+  f3 o, d, idir;
+  float tmin;
+  uint32_t oct;
+  uint2 group;
+  int sp;
   Hit hit;
-  hit.t = tmax; hit.leaf = -1; hit.b1 = 0.f; hit.b2 = 0.f;
 
-  const uint32_t oct = (d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u);
-  const uint32_t octinv = oct ^ 7u;
-  f3 idir;
-  idir.x = 1.0f / (fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x));
-  idir.y = 1.0f / (fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y));
-  idir.z = 1.0f / (fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z));
+  __device__ inline void begin(f3 o_, f3 d_, float tmin_, float tmax_) {
+    o = o_; d = d_; tmin = tmin_;
+    hit.t = tmax_; hit.leaf = -1; hit.b1 = 0.f; hit.b2 = 0.f;
+    oct = (d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u);
+    idir.x = 1.0f / (fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x));
+    idir.y = 1.0f / (fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y));
+    idir.z = 1.0f / (fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z));
+    sp = 0;
+    group = make_uint2(0u, 0x80000000u);  // root: node 0, top priority bit
+  }
 
-  uint2 stack[BDPT_STACK];
-  int sp = 0;
-  uint2 group = make_uint2(0u, 0x80000000u);  // root: node 0, top priority bit
-
-  for (;;) {
+  // `stack` is the caller's per-thread array of BDPT_STACK entries (kept out of this struct so that the
+  // scalar state stays in registers)
+  template <bool ANY_HIT>
+  __device__ inline bool step(const DScene& sc, uint2* stack) {
+    const uint32_t octinv = oct ^ 7u;
     // ---- pop the nearest internal child of the current group
     uint32_t bit = 31u - (uint32_t)__clz(group.y);
     group.y &= ~(1u << bit);
@@ -134,16 +145,24 @@ __device__ inline Hit traverse(const DScene& sc, f3 o, f3 d, float tmin, float t
       int k = (int)q1.y + i;
       if (intersect_prim(sc.prims, k, o, d, tmin, hit.t, hit.b1, hit.b2)) {
         hit.leaf = k;
-        if (ANY_HIT) return hit;
+        if (ANY_HIT) return true;
       }
     }
-
     if (group.y <= 0x00ffffffu) {
-      if (sp == 0) break;
+      if (sp == 0) return true;
       group = stack[--sp];
     }
+    return false;
   }
-  return hit;
+};
+
+template <bool ANY_HIT>
+__device__ inline Hit traverse(const DScene& sc, f3 o, f3 d, float tmin, float tmax) {
+  Trav T;
+  uint2 stack[BDPT_STACK];
+  T.begin(o, d, tmin, tmax);
+  while (!T.template step<ANY_HIT>(sc, stack)) {}
+  return T.hit;
 }
 
 // Shading data of an accepted closest hit: interpolated (unflipped) unit normal, primitive id in
