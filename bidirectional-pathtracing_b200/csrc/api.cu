@@ -34,6 +34,7 @@ struct BdptContext {
   uint4* d_nodes = nullptr;
   float4 *d_prims = nullptr, *d_shading = nullptr, *d_mats = nullptr, *d_lights = nullptr;
   double* d_prims64 = nullptr;
+  size_t cap_scene[6] = {0, 0, 0, 0, 0, 0};
   uint32_t bvh_nodes = 0, bvh_depth = 0;
   double ms_bvh_build = 0;
 
@@ -405,14 +406,22 @@ int bdpt_upload_scene(BdptContext* ctx, const BdptCamera* camera, const BdptMate
   }
 
   CK(cudaStreamSynchronize(ctx->stream));
-  dfree(ctx->d_nodes); dfree(ctx->d_prims); dfree(ctx->d_shading); dfree(ctx->d_mats); dfree(ctx->d_lights); dfree(ctx->d_prims64);
-  CK(cudaMalloc(&ctx->d_nodes, bvh.nodes.size() * sizeof(uint32_t)));
-  CK(cudaMalloc(&ctx->d_prims, hp.size() * sizeof(float4)));
-  CK(cudaMalloc(&ctx->d_shading, hs.size() * sizeof(float4)));
-  CK(cudaMalloc(&ctx->d_prims64, h64.size() * sizeof(double)));
+  // grow-only device storage: re-uploading a scene of the same size allocates nothing
+  auto ensure = [&](void** p, size_t* cap, size_t bytes) -> cudaError_t {
+    if (bytes <= *cap && *p) return cudaSuccess;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaSuccess) *cap = bytes;
+    return e;
+  };
+  CK(ensure((void**)&ctx->d_nodes, &ctx->cap_scene[0], bvh.nodes.size() * sizeof(uint32_t)));
+  CK(ensure((void**)&ctx->d_prims, &ctx->cap_scene[1], hp.size() * sizeof(float4)));
+  CK(ensure((void**)&ctx->d_shading, &ctx->cap_scene[2], hs.size() * sizeof(float4)));
+  CK(ensure((void**)&ctx->d_mats, &ctx->cap_scene[3], hm.size() * sizeof(float4)));
+  CK(ensure((void**)&ctx->d_lights, &ctx->cap_scene[4], hl.size() * sizeof(float4)));
+  CK(ensure((void**)&ctx->d_prims64, &ctx->cap_scene[5], h64.size() * sizeof(double)));
   CK(cudaMemcpyAsync(ctx->d_prims64, h64.data(), h64.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMalloc(&ctx->d_mats, hm.size() * sizeof(float4)));
-  CK(cudaMalloc(&ctx->d_lights, hl.size() * sizeof(float4)));
   CK(cudaMemcpyAsync(ctx->d_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_prims, hp.data(), hp.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_shading, hs.data(), hs.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
