@@ -1,0 +1,38 @@
+"""ctypes binding of libbdpt_host.so (include/bdpt_host.h): the C++ .dae loader of the host side."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import flatscene as fs
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "host", "libbdpt_host.so")
+_lib = None
+
+
+def load_library():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `make -C bidirectional-pathtracing_b200/host`")
+        L = C.CDLL(LIB_PATH)
+        L.bdpt_host_load_dae.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_ubyte)), C.POINTER(C.c_size_t)]
+        L.bdpt_host_load_dae.restype = C.c_int
+        L.bdpt_host_free.argtypes = [C.c_void_p]
+        L.bdpt_host_free.restype = None
+        L.bdpt_host_last_error.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def load_dae(path: str, width: int = 0, height: int = 0) -> fs.FlatScene:
+    """COLLADA file -> flat scene, by the C++ loader (reference semantics: camera placed at 800x600; `-r` optional)."""
+    L = load_library()
+    blob, size = C.POINTER(C.c_ubyte)(), C.c_size_t()
+    rc = L.bdpt_host_load_dae(os.fsencode(path), width, height, C.byref(blob), C.byref(size))
+    if rc != 0:
+        raise RuntimeError(f"bdpt_host_load_dae({path}) failed ({rc}): {L.bdpt_host_last_error().decode()}")
+    try:
+        return fs.frombytes(C.string_at(blob, size.value))
+    finally:
+        L.bdpt_host_free(blob)

@@ -1,0 +1,24 @@
+// dae_scene.h — host-side scene ingest: COLLADA (.dae + CGL profile) -> flat POD scene.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/bdpt_flatscene.h"
+
+namespace bdpt_host {
+
+struct FlatSceneData {
+  BdptCamera camera;
+  std::vector<BdptMaterial> materials;
+  std::vector<BdptLight> lights;
+  std::vector<BdptPrim> prims;
+};
+
+// Loads a scene the way the reference's `pathtracer` does before `-r` is applied (camera at 800x600).
+bool load_dae(const std::string& path, FlatSceneData* out, std::string* err);
+// Camera::set_screen_size (reference camera.cpp:83-89): what `-r W H` does to the camera.
+void apply_screen_size(BdptCamera* cam, int w, int h);
+// The ".fscene" byte layout of include/bdpt_flatscene.h.
+std::vector<unsigned char> serialize(const FlatSceneData& s);
+
+}  // namespace bdpt_host

@@ -1,0 +1,31 @@
+// host_api.cpp — C entry points of libbdpt_host.so (include/bdpt_host.h): the .dae loader as a library,
+// so that the ingest path can be tested against the reference's own loader without a GPU.
+#include "../../include/bdpt_host.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "dae_scene.h"
+
+namespace { thread_local std::string g_err; }
+
+extern "C" {
+
+int bdpt_host_load_dae(const char* path, int width, int height, unsigned char** blob, size_t* size) {
+  if (!path || !blob || !size) return -2;
+  bdpt_host::FlatSceneData s;
+  if (!bdpt_host::load_dae(path, &s, &g_err)) return -3;
+  if (width > 0 && height > 0) bdpt_host::apply_screen_size(&s.camera, width, height);
+  std::vector<unsigned char> b = bdpt_host::serialize(s);
+  *blob = (unsigned char*)malloc(b.size());
+  if (!*blob) { g_err = "out of memory"; return -2; }
+  memcpy(*blob, b.data(), b.size());
+  *size = b.size();
+  return 0;
+}
+
+void bdpt_host_free(void* p) { free(p); }
+const char* bdpt_host_last_error(void) { return g_err.c_str(); }
+
+}  // extern "C"

@@ -154,7 +154,7 @@ int cmd_dump(int argc, char** argv) {
     BSDF* b = mats[i];
     if (auto* d = dynamic_cast<DiffuseBSDF*>(b)) { o.type = BDPT_MAT_DIFFUSE; put3(o.reflectance, d->reflectance); }
     else if (auto* e = dynamic_cast<EmissionBSDF*>(b)) { o.type = BDPT_MAT_EMISSION; put3(o.radiance, e->radiance); }
-    else if (auto* mi = dynamic_cast<MirrorBSDF*>(b)) { o.type = BDPT_MAT_MIRROR; put3(o.reflectance, mi->reflectance); o.roughness = mi->roughness; }
+    else if (auto* mi = dynamic_cast<MirrorBSDF*>(b)) { o.type = BDPT_MAT_MIRROR; put3(o.reflectance, mi->reflectance); /* MirrorBSDF::roughness is never initialised (bsdf.h:214): not recorded */ }
     else if (auto* g = dynamic_cast<GlassBSDF*>(b)) { o.type = BDPT_MAT_GLASS; put3(o.reflectance, g->reflectance); put3(o.transmittance, g->transmittance); o.ior = g->ior; o.roughness = g->roughness; }
     else if (auto* r = dynamic_cast<RefractionBSDF*>(b)) { o.type = BDPT_MAT_REFRACTION; put3(o.transmittance, r->transmittance); o.ior = r->ior; o.roughness = r->roughness; }
     else if (auto* mf = dynamic_cast<MicrofacetBSDF*>(b)) { o.type = BDPT_MAT_MICROFACET; put3(o.eta, mf->eta); put3(o.k, mf->k); o.alpha = mf->alpha; }

@@ -1,0 +1,178 @@
+"""The C++ scene ingest (bidirectional-pathtracing_b200/host/dae_scene.cpp, via libbdpt_host.so) against the
+flat scenes the REFERENCE'S OWN loader produced (tests/golden/scenes/*.fscene.gz, dumped by
+oracle/ref_harness.cpp from ColladaParser + Application::load + get_static_scene + build_accel).
+The comparison is byte for byte: positions, half-edge vertex normals, primitive order, materials,
+lights and the placed camera."""
+import os
+import struct
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, load_scene
+
+DAE_DIRS = ["/root/reference/dae/sky", os.path.join(ROOT, "oracle", "_ref", "scenes")]
+CASES = {  # fixture name -> .dae file name(s) to look for
+    "CBspheres_lambertian": ["CBspheres_lambertian.dae"],
+    "CBspheres": ["CBspheres.dae"],
+    "CBgems": ["CBgems.dae"],
+    "CBempty": ["CBempty.dae"],
+    "CBbunny": ["CBbunny.dae"],
+    "CBcoil": ["CBcoil.dae"],
+    "CBspheres_lambertian_occluded": ["../ben/CBspheres_lambertian.dae", "CBspheres_lambertian_occluded.dae"],
+}
+
+
+def find_dae(names):
+    for d in DAE_DIRS:
+        for n in names:
+            p = os.path.normpath(os.path.join(d, n))
+            if os.path.exists(p):
+                return p
+    return None
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_loader_reproduces_reference_scene_bytes(name):
+    from bdpt import host
+    dae = find_dae(CASES[name])
+    if dae is None:
+        pytest.skip("no .dae input on this box (reference tree and oracle/_ref/scenes both absent)")
+    got, ref = host.load_dae(dae), load_scene(name)
+    assert got.n_prims == ref.n_prims
+    for part in ("camera", "materials", "lights", "prims"):
+        assert getattr(got, part).tobytes() == getattr(ref, part).tobytes(), part
+
+
+def test_loader_applies_screen_size():
+    from bdpt import host
+    dae = find_dae(CASES["CBspheres"])
+    if dae is None:
+        pytest.skip("no .dae input on this box")
+    a = host.load_dae(dae, 480, 360)
+    b = load_scene("CBspheres").with_frame(480, 360)
+    assert a.camera.tobytes() == b.camera.tobytes()
+
+
+MINI = """<?xml version="1.0" encoding="utf-8"?>
+<!-- a hand-written Y_UP scene: one quad floor (a polygon with 4 vertices), a sphere, a point light -->
+<COLLADA xmlns="http://www.collada.org/2005/11/COLLADASchema" version="1.4.1">
+  <asset><up_axis>Y_UP</up_axis></asset>
+  <library_cameras><camera id="cam" name="cam"><optics><technique_common><perspective>
+    <xfov>40</xfov><aspect_ratio>1.3333</aspect_ratio><znear>0.1</znear><zfar>100</zfar>
+  </perspective></technique_common></optics></camera></library_cameras>
+  <library_lights><light id="L" name="L"><technique_common><point><color>3 2 1</color>
+    <constant_attenuation>1</constant_attenuation><linear_attenuation>0</linear_attenuation><quadratic_attenuation>0</quadratic_attenuation>
+  </point></technique_common></light></library_lights>
+  <library_effects><effect id="fx"><profile_COMMON><technique sid="common"><phong>
+    <diffuse><color sid="diffuse">0.25 0.5 0.75 1</color></diffuse></phong></technique></profile_COMMON></effect>
+    <effect id="glassfx"><profile_COMMON><technique sid="common"><phong><diffuse><color>1 1 1 1</color></diffuse></phong></technique></profile_COMMON>
+      <extra><technique profile="CGL"><glass><transmittance>1 1 1</transmittance><reflectance>1 1 1</reflectance><roughness>0</roughness><ior>1.5</ior></glass></technique></extra></effect>
+  </library_effects>
+  <library_materials><material id="mat" name="mat"><instance_effect url="#fx"/></material>
+    <material id="glass" name="glass"><instance_effect url="#glassfx"/></material></library_materials>
+  <library_geometries>
+    <geometry id="floor" name="floor"><mesh>
+      <source id="floor-pos"><float_array id="floor-pos-array" count="12">-1 0 -1 -1 0 1 1 0 1 1 0 -1</float_array></source>
+      <vertices id="floor-vtx"><input semantic="POSITION" source="#floor-pos"/></vertices>
+      <polylist material="mat" count="1"><input semantic="VERTEX" source="#floor-vtx" offset="0"/><vcount>4</vcount><p>0 1 2 3</p></polylist>
+    </mesh></geometry>
+    <geometry id="ball" name="ball"><extra><technique profile="CGL"><sphere><radius>0.25</radius></sphere></technique></extra></geometry>
+  </library_geometries>
+  <library_visual_scenes><visual_scene id="Scene">
+    <node id="n_cam" name="cam"><matrix>1 0 0 0 0 1 0 1 0 0 1 5 0 0 0 1</matrix><instance_camera url="#cam"/></node>
+    <node id="n_light" name="light"><matrix>1 0 0 0 0 1 0 2 0 0 1 0 0 0 0 1</matrix><instance_light url="#L"/></node>
+    <node id="n_floor" name="floor"><matrix>2 0 0 0 0 1 0 0 0 0 2 0 0 0 0 1</matrix><instance_geometry url="#floor">
+      <bind_material><technique_common><instance_material symbol="mat" target="#mat"/></technique_common></bind_material></instance_geometry></node>
+    <node id="n_ball" name="ball"><matrix>2 0 0 0.5 0 2 0 0.5 0 0 2 0 0 0 0 1</matrix><instance_geometry url="#ball">
+      <bind_material><technique_common><instance_material symbol="glass" target="#glass"/></technique_common></bind_material></instance_geometry></node>
+  </visual_scene></library_visual_scenes>
+  <scene><instance_visual_scene url="#Scene"/></scene>
+</COLLADA>
+"""
+
+
+def test_hand_written_scene(tmp_path):
+    from bdpt import flatscene as fs, host
+    p = tmp_path / "mini.dae"
+    p.write_text(MINI)
+    sc = host.load_dae(str(p))
+    assert sc.n_prims == 2 and len(sc.materials) == 2 and len(sc.lights) == 1
+    tri, sph = sc.prims[0], sc.prims[1]
+    # a quad contributes only the triangle (v[n-1], v[0], v[1]) (object.cpp:36-41)
+    assert tri["type"] == fs.PRIM_TRIANGLE
+    assert np.allclose(tri["data"][:9], [2, 0, -2, -2, 0, -2, -2, 0, 2])
+    assert np.allclose(np.abs(tri["data"][9:].reshape(3, 3)), [[0, 1, 0]] * 3)
+    assert sph["type"] == fs.PRIM_SPHERE and np.allclose(sph["data"][:4], [0.5, 0.5, 0.0, 0.5])   # radius * |M e_x|
+    assert sc.materials[0]["type"] == fs.MAT_DIFFUSE and np.allclose(sc.materials[0]["reflectance"], [0.25, 0.5, 0.75])
+    assert sc.materials[1]["type"] == fs.MAT_GLASS and sc.materials[1]["ior"] == np.float32(1.5)
+    assert sc.lights[0]["type"] == fs.LIGHT_POINT and np.allclose(sc.lights[0]["position"], [0, 2, 0])
+    cam = sc.camera[0]
+    # placed looking at the bbox centroid from direction unit(M (0,0,-1,1)) at 1.5 |bbox diagonal|
+    target = np.array([0.0, 0.5, 0.0])
+    assert np.allclose(cam["target"], target)
+    dirc = np.array([0, 1, 4.0]); dirc /= np.linalg.norm(dirc)
+    diag = np.linalg.norm([4, 1, 4])
+    assert np.allclose(cam["pos"], target + dirc * diag * 1.5, atol=1e-9)
+    assert cam["screen_w"] == 800 and cam["screen_h"] == 600
+
+
+def test_loader_errors(tmp_path):
+    from bdpt import host
+    with pytest.raises(RuntimeError, match="cannot open"):
+        host.load_dae(str(tmp_path / "missing.dae"))
+    bad = tmp_path / "bad.dae"
+    bad.write_text("<notcollada/>")
+    with pytest.raises(RuntimeError, match="not a COLLADA"):
+        host.load_dae(str(bad))
+    spot = tmp_path / "dir.dae"
+    spot.write_text(MINI.replace("<point><color>3 2 1</color>", "<directional><color>3 2 1</color>").replace("</point>", "</directional>"))
+    with pytest.raises(RuntimeError, match="light type not supported"):
+        host.load_dae(str(spot))
+    nocam = tmp_path / "nocam.dae"
+    nocam.write_text(MINI.replace('<instance_camera url="#cam"/>', ""))
+    with pytest.raises(RuntimeError, match="no camera"):
+        host.load_dae(str(nocam))
+
+
+def read_png(path):
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, w, h = 8, b"", 0, 0
+    while pos < len(raw):
+        n, typ = struct.unpack(">I4s", raw[pos:pos + 8])
+        body = raw[pos + 8:pos + 8 + n]
+        assert struct.unpack(">I", raw[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(typ + body)
+        if typ == b"IHDR":
+            w, h, depth, ctype = struct.unpack(">IIBB", body[:10])
+            assert (depth, ctype) == (8, 6)
+        elif typ == b"IDAT":
+            idat += body
+        pos += 12 + n
+    px = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 1 + 4 * w)
+    assert (px[:, 0] == 0).all()
+    return px[:, 1:].reshape(h, w, 4)
+
+
+@pytest.mark.gpu
+def test_cli_renders_like_the_library(tmp_path):
+    """`pathtracer -s -m -r -f` end to end: .dae -> PNG equals the image the library tone-maps for the same scene."""
+    from bdpt import api
+    dae = find_dae(CASES["CBspheres"])
+    if dae is None:
+        pytest.skip("no .dae input on this box")
+    exe = os.path.join(ROOT, "bidirectional-pathtracing_b200", "host", "pathtracer")
+    out = tmp_path / "cli.png"
+    r = subprocess.run([exe, "-t", "8", "-s", "16", "-m", "5", "-r", "160", "120", "-f", str(out), dae], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Rendering... 100%!" in r.stdout and "million rays per second" in r.stdout
+    img = read_png(str(out))
+    R = api.Renderer(0, ns_aa=16, max_ray_depth=5, seed=0)
+    R.set_scene(load_scene("CBspheres")); R.set_frame_size(160, 120); R.render()
+    ref = R.tonemap(0)
+    assert img.shape == ref.shape == (120, 160, 4)
+    assert np.mean(np.abs(img.astype(int) - ref.astype(int)) <= 1) > 0.999
+    rate = read_png(str(out)[:-4] + "_rate.png")
+    assert (rate[..., 0] == 255).all() and (rate[..., 1:3] == 0).all()
