@@ -44,11 +44,27 @@ CONFIGS = {
     "config1": ("CBspheres", "CBspheres", 480, 360, 128, 5, 0, "configs[1] CBspheres 480x360 128spp m=5"),
     "config2": ("CBbunny", "CBbunny", 1024, 768, 1024, 5, 0,
                 "configs[2] CBlucy 1024x768 1024spp m=5 on the CBbunny stand-in (CBlucy.dae absent from the reference checkout)"),
+    "config2x4": ("dae:CBbunny4", "CBbunny4", 1024, 768, 1024, 5, 0,
+                  "configs[2] CBlucy 1024x768 1024spp m=5 on the CBlucy-class stand-in CBbunny4 (bunny refined to 114,304 triangles by scripts/make_standin.py)"),
+    "config2x16": ("dae:CBbunny16", "CBbunny16", 1024, 768, 1024, 5, 0,
+                   "configs[2] CBlucy 1024x768 1024spp m=5 on CBbunny16 (bunny refined to 457,216 triangles by scripts/make_standin.py)"),
     "config3": ("CBgems", "CBgems", 1024, 768, 1024, 16, 1, "configs[3] CBgems 1024x768 1024spp m=16 roulette"),
     "config4": ("CBbunny", "CBbunny", 1920, 1080, 4096, 8, 0, "configs[4] CBlucy 1920x1080 4096spp m=8 on the CBbunny stand-in"),
 }
 DEFAULT_CONFIG = "config2"
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def load_fixture(fixture):
+    """Committed flat-scene fixture, or `dae:<name>`: a staged .dae read by the C++ loader (libbdpt_host.so)."""
+    from bdpt import flatscene as fs
+    if fixture.startswith("dae:"):
+        from bdpt import host
+        path = os.path.join(ROOT, "oracle", "_ref", "scenes", fixture[4:] + ".dae")
+        if not os.path.exists(path):
+            raise SystemExit(f"{path} is missing: run `python scripts/make_standin.py` where /root/reference is mounted")
+        return host.load_dae(path)
+    return fs.load(os.path.join(ROOT, "tests", "golden", "scenes", fixture + ".fscene.gz"))
 
 
 def hbm_peak():
@@ -142,8 +158,7 @@ def reference_baseline(cfg):
         return {"value": v, "unit": "samples/s", "cores": cores, "kind": "reference",
                 "sample": f"pathtracer_ref -t {cores} -s {s} -m {m} -r {W} {H} {dae}.dae ({W * H * s} samples, {secs:.2f} s; "
                           f"time is linear in spp, SURVEY.md §6)"}
-    from bdpt import flatscene as fs
-    sc = fs.load(os.path.join(ROOT, "tests", "golden", "scenes", fixture + ".fscene.gz"))
+    sc = load_fixture(fixture)
     orc = O.Oracle(sc, W, H)
     t0 = time.time()
     orc.render(s, m, rng_mode=1, threads=cores, roulette=roulette)
@@ -201,7 +216,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     fixture, dae, W, H, spp, m, roulette, desc = cfg
-    scene = fs.load(os.path.join(ROOT, "tests", "golden", "scenes", fixture + ".fscene.gz"))
+    scene = load_fixture(fixture)
     first, n_mine = shard.shard_samples(spp, rank, world)
 
     R = api.Renderer(local, ns_aa=spp, max_ray_depth=m, seed=0, roulette=bool(roulette))
@@ -258,7 +273,7 @@ def main():
     clock_info = clocks.stop() if rank == 0 else None
     value = samples_per_step * args.steps / (ms / 1e3)
     launches = (st["kernel_launches"] + 0) * 1  # launches of the last step (stats are cleared each step)
-    gpu_launches = int(launches) * args.steps
+    gpu_launches = int(launches) * args.steps * world   # every rank launches the same kernels
 
     # end to end through the C-ABI from host buffers
     for _ in range(1):

@@ -65,6 +65,7 @@ struct BdptContext {
   int sched = -1, sched_req = -1;
   int variant = 1;      // scheduling-threshold variant of k_walk_pt (BDPT_VARIANT, tuning only)
   int connect_minb = 6; // __launch_bounds__ min blocks of k_connect (BDPT_CONNECT_MINB, tuning only)
+  int batch_log2 = 22, batch_gib = 12;  // batch size cap (samples) and its memory budget (BDPT_BATCH_LOG2, BDPT_BATCH_GIB)
   int walk_ctas = 4, shadow_ctas = 8;  // resident CTAs per SM of the persistent kernels
 };
 
@@ -300,6 +301,8 @@ int bdpt_create(int device, BdptContext** out) {
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (const char* e = getenv("BDPT_SCHED")) ctx->sched_req = atoi(e);
   ctx->sched = ctx->sched_req >= 0 ? ctx->sched_req : 1;
+  if (const char* e = getenv("BDPT_BATCH_LOG2")) ctx->batch_log2 = std::min(24, std::max(10, atoi(e)));
+  if (const char* e = getenv("BDPT_BATCH_GIB")) ctx->batch_gib = std::min(64, std::max(1, atoi(e)));
   if (const char* e = getenv("BDPT_CONNECT_MINB")) ctx->connect_minb = atoi(e);
   if (const char* e = getenv("BDPT_VARIANT")) ctx->variant = atoi(e);
   if (const char* e = getenv("BDPT_WALK_CTAS")) ctx->walk_ctas = std::max(1, atoi(e));
@@ -493,8 +496,8 @@ int bdpt_render(BdptContext* ctx, const BdptRenderParams* p) {
   // batch size: bounded by the vertex planes (64 B/vertex) and the worst-case shadow queue (48 B/entry)
   const int m = std::max(1, p->max_ray_depth);
   const size_t per_sample = (size_t)2 * (m + 1) * 64 + (size_t)(m + 1) * (m + 1) * 48 + 8;
-  size_t B = (size_t)(3ull << 30) / per_sample;
-  B = std::min<size_t>(B, 1u << 20);
+  size_t B = (size_t)((size_t)ctx->batch_gib << 30) / per_sample;
+  B = std::min<size_t>(B, (size_t)1 << ctx->batch_log2);
   B = std::max<size_t>(B & ~(size_t)1023, 1024);
   const int tiles_x = (ctx->W + 7) / 8, npix_pad = tiles_x * ((ctx->H + 3) / 4) * 32;
   const unsigned long long total = (unsigned long long)npix_pad * (unsigned long long)p->n_samples;
