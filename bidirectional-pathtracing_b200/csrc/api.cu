@@ -234,10 +234,8 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
   const unsigned cgrid = (unsigned)((J.B + threads - 1) / threads) * (unsigned)(J.m + 1);
   switch (TRACE ? 0 : ctx->connect_minb) {
     case 4: k_connect<TRACE, 4><<<cgrid, threads, 0, ctx->stream>>>(J); break;
-    case 5: k_connect<TRACE, 5><<<cgrid, threads, 0, ctx->stream>>>(J); break;
     case 6: k_connect<TRACE, 6><<<cgrid, threads, 0, ctx->stream>>>(J); break;
     case 8: k_connect<TRACE, 8><<<cgrid, threads, 0, ctx->stream>>>(J); break;
-    case 10: k_connect<TRACE, 10><<<cgrid, threads, 0, ctx->stream>>>(J); break;
     default: k_connect<TRACE, 3><<<cgrid, threads, 0, ctx->stream>>>(J); break;
   }
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 2), ctx->stream);

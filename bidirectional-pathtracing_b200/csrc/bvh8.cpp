@@ -7,6 +7,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <deque>
 
 namespace bdpt {
@@ -38,7 +39,8 @@ struct Builder {
   std::vector<float> cent;  // 3 per prim
   std::vector<BNode> bn;
   static constexpr int kBins = 16;
-  static constexpr int kMaxLeaf = 3;
+  int kMaxLeaf = 3;        // primitives per leaf child (<= 3: the node's meta byte counts them in unary)
+  float kTravCost = 0.5f;  // SAH cost of one more traversal step relative to one primitive test
 
   explicit Builder(const std::vector<BuildPrim>& p) : prims(p) {
     idx.resize(p.size());
@@ -48,6 +50,8 @@ struct Builder {
       for (int a = 0; a < 3; a++) cent[3 * i + a] = 0.5f * (p[i].lo[a] + p[i].hi[a]);
     }
     bn.reserve(p.size() * 2 + 1);
+    if (const char* e = getenv("BDPT_BVH_LEAF")) kMaxLeaf = std::max(1, std::min(3, atoi(e)));   // tuning knobs
+    if (const char* e = getenv("BDPT_BVH_CT")) kTravCost = (float)atof(e);
   }
 
   int build(int first, int count) {
@@ -91,7 +95,7 @@ struct Builder {
     float area = n.box.half_area();
     if (count <= kMaxLeaf) {
       float leaf_cost = area * count;
-      float split_cost = best_axis < 0 ? FLT_MAX : 0.5f * area + best_cost;
+      float split_cost = best_axis < 0 ? FLT_MAX : kTravCost * area + best_cost;
       if (leaf_cost <= split_cost) return me;
     }
     int mid;

@@ -222,17 +222,17 @@ __device__ inline Vtx unpack(const VRaw& r) {
   return v;
 }
 
-// Grid: 1-D, the (m+1) values of t of one group of 128 samples are consecutive blocks, so the light
-// vertices those blocks share are fetched from DRAM once and found in L2 by the other m.  Inside the
-// s loop nothing is prefetched: holding a second vertex costs 33 registers and an occupancy step.
-template <bool TRACE, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_connect(const Job J) {
-  const int t = (int)(blockIdx.x % (unsigned)(J.m + 1)) + 1;
-  const int si = (int)(blockIdx.x / (unsigned)(J.m + 1)) * blockDim.x + threadIdx.x;
-  if (si >= J.B) return;
-  const int nE = J.counts[si];
-  const int nL = J.counts[J.B + si];
-  if (nE == 0 || t > nE) return;  // invalid lane or the eye subpath is shorter than t
+// Where k_connect's threads find the vertices of their sample.  (A variant that staged a block's vertices
+// in shared memory first — S samples x (m+1) threads per block — measured 2.3x SLOWER on B200: blocks then
+// live as long as their slowest t, and the occupancy lost to that outweighs the latency saved.)
+struct GlobalVerts {
+  const Job& J; int si;
+  __device__ inline Vtx get(int kind, int j) const { return load_vtx(J, kind, j, si); }
+  __device__ inline void light_origin(float4* a, float4* b) const { size_t s1 = VSLOT(J, 1, 1, si); *a = J.v0[s1]; *b = J.v1[s1]; }
+};
+// All strategies (s = 0 .. nL) of one (sample, t): estimate_bidirection_radiance + the closed-form MIS weight.
+template <bool TRACE, class VERTS>
+__device__ inline void connect_strategies(const Job& J, const int si, const int t, const int nL, const VERTS& V) {
   int x, y, sample;
   decode_sample(J, J.g0 + (unsigned long long)si, &x, &y, &sample);
   const DScene& sc = J.sc;
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(128, MINB) k_connect(const Job J) {
   Vtx E; Mat ME; Frame frE;
   E.mat = -1; E.D = 1.f; E.S = 0.f; E.q = 1.f;
   if (t >= 2) {
-    E = load_vtx(J, 0, t, si);
+    E = V.get(0, t);
     ME = load_mat(sc, E.mat);
     frE = make_frame(E.n);
   } else {
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(128, MINB) k_connect(const Job J) {
         float tail = 0.f;
         bool delta_prev = false;
         if (t >= 3) {
-          Vtx P = load_vtx(J, 0, t - 1, si);
+          Vtx P = V.get(0, t - 1);
           delta_prev = type_is_delta(mat_type(sc, P.mat));
           if (P.S > 0.f) {
             float pp, dp;
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(128, MINB) k_connect(const Job J) {
         Lv.mat = -1; Lv.q = 1.f; Lv.D = pA; Lv.S = 1.f; Lv.wo = zero;
         ML.type = -1;
       } else {
-        Lv = load_vtx(J, 1, s, si);
+        Lv = V.get(1, s);
         ML = load_mat(sc, Lv.mat);
       }
       if (s >= 2) frL = make_frame(Lv.n);
@@ -353,8 +353,8 @@ __global__ void __launch_bounds__(128, MINB) k_connect(const Job J) {
           winv += (double)r_s * (double)r_s * (double)Lv.S;
         } else {
           // s == 1: the chain is evaluated at the ORIGINAL light-subpath origin
-          size_t s1 = VSLOT(J, 1, 1, si);
-          const float4 a = J.v0[s1], b = J.v1[s1];   // light_path[1]
+          float4 a, b;   // light_path[1]
+          V.light_origin(&a, &b);
           f3 wv = mk3(a.x, a.y, a.z) - ve_pos;
           float d2 = dot(wv, wv);
           f3 wd = wv * rsqrtf(d2);
@@ -389,6 +389,20 @@ __global__ void __launch_bounds__(128, MINB) k_connect(const Job J) {
   }
   unsigned int tot = __reduce_add_sync(__activemask(), nconn);
   if ((threadIdx.x & 31) == (__ffs(__activemask()) - 1)) atomicAdd(J.stats + 2, (unsigned long long)tot);
+}
+
+// One thread per (sample, t), vertices read from HBM/L2 as needed.  Grid: 1-D, the (m+1) values of t of
+// one group of 128 samples are consecutive blocks, so the light vertices they share meet in L2.
+template <bool TRACE, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_connect(const Job J) {
+  const int t = (int)(blockIdx.x % (unsigned)(J.m + 1)) + 1;
+  const int si = (int)(blockIdx.x / (unsigned)(J.m + 1)) * blockDim.x + threadIdx.x;
+  if (si >= J.B) return;
+  const int nE = J.counts[si];
+  const int nL = J.counts[J.B + si];
+  if (nE == 0 || t > nE) return;  // invalid lane or the eye subpath is shorter than t
+  GlobalVerts V{J, si};
+  connect_strategies<TRACE>(J, si, t, nL, V);
 }
 
 // -------------------------------------------------------------------------------------- shadow
