@@ -308,7 +308,10 @@ def main():
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get(top)
+                tj = json.load(open(tp))
+                traffic = tj.get(top)
+                if traffic is not None and tj.get("batch_samples") and tj["batch_samples"] != B:
+                    traffic = traffic * B / tj["batch_samples"]   # captured at another batch size: scale per sample
             except Exception:
                 traffic = None
         line = {
