@@ -23,6 +23,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libbdpt_b200.so")
 
 BUFFER_SUM, BUFFER_EYE, BUFFER_LIGHT = 0, 1, 2
 FLAG_ROULETTE = 1
+FLAG_NO_MIS = 2
 
 
 class BdptError(RuntimeError):
@@ -101,7 +102,7 @@ class Renderer:
     """One GPU, one scene, one frame.  Mirrors the reference's RaytracedRenderer for the BDPT path."""
 
     def __init__(self, device: int = 0, *, ns_aa: int = 1, max_ray_depth: int = 1, seed: int = 0,
-                 roulette: bool = False):
+                 roulette: bool = False, no_mis: bool = False):
         self.L = load_library()
         self.h = C.c_void_p()
         rc = self.L.bdpt_create(device, C.byref(self.h))
@@ -114,6 +115,7 @@ class Renderer:
         self.max_ray_depth = max_ray_depth
         self.seed = seed
         self.roulette = roulette
+        self.no_mis = no_mis
         self.W = self.H = 0
         self._keep = None
 
@@ -161,7 +163,7 @@ class Renderer:
         p.max_ray_depth = self.max_ray_depth
         p.first_sample = first_sample
         p.n_samples = self.ns_aa if n_samples is None else n_samples
-        p.flags = FLAG_ROULETTE if self.roulette else 0
+        p.flags = (FLAG_ROULETTE if self.roulette else 0) | (FLAG_NO_MIS if self.no_mis else 0)
         p.only_t, p.only_s = strategy if strategy else (-1, -1)
         p.seed = self.seed
         return p

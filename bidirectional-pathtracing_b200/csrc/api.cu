@@ -194,6 +194,7 @@ void fill_job(BdptContext* ctx, const BdptRenderParams* p, Job* J) {
   J->tiles_x = (ctx->W + 7) / 8;
   J->npix_pad = J->tiles_x * ((ctx->H + 3) / 4) * 32;
   J->roulette = (p->flags & BDPT_FLAG_ROULETTE) ? 1 : 0;
+  J->no_mis = (p->flags & BDPT_FLAG_NO_MIS) ? 1 : 0;
   J->only_t = p->only_t; J->only_s = p->only_s;
   J->single_x = -1; J->single_y = -1;
 }

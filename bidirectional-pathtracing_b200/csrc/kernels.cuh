@@ -53,6 +53,7 @@ struct Job {
   int first_sample;           // sample index of job-sample 0
   int tiles_x, npix_pad;      // 8x4 pixel tiles per row; padded pixel count
   int roulette;
+  int no_mis;                 // weight 1 for every strategy: the reference's own debug switch (bidirection.cpp:124-126)
   int only_t, only_s;
   int single_x, single_y;     // >= 0: the job is this one pixel (trace mode)
 };
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(128) k_walk(const Job J) {
     const bool delta_j = type_is_delta(M.type);
     const float D_j = (kind == 0 && j == 2) ? 1.f : pdfeval_prev * g;
     const f3 zero = mk3(0.f);
-    const float D_rev = bsdf_pdf(M, zero, w_out) * p_keep * g;  // density of (j -> j-1) as the chains use it
+    const float D_rev = bsdf_pdf_mis(M, wi, w_out) * p_keep * g;  // density of (j -> j-1) as the chains use it
     float S_j = (delta_j || delta_prev) ? 0.f : 1.f;
     if (S_prev > 0.f) { float R = D_rev / D_prev; S_j += R * R * S_prev; }
     S_j = clampS(S_j);
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(128) k_walk(const Job J) {
     if (J.roulette && !(rng.uniform() < p_keep)) break;
     if (is_zero(f)) break;  // throughput is exactly zero from here on: later vertices add nothing
 
-    pdfeval_prev = bsdf_pdf(M, zero, wi) * p_keep;
+    pdfeval_prev = bsdf_pdf_mis(M, w_out, wi) * p_keep;
     prev_f = f; prev_n = n; prev_pdf = pdf * p_keep;
     D_prev = D_j; S_prev = S_j; delta_prev = delta_j;
     o = hit_p; d = wi_world; tmin = BDPT_EPS_F; tmax = INFINITY;
@@ -290,7 +291,7 @@ __device__ inline void connect_strategies(const Job& J, const int si, const int 
           }
         }
         double winv = 1.0 + (double)r_t * (double)r_t * ((double)(delta_prev ? 0.f : 1.f) + (double)tail);
-        w = (float)(1.0 / winv);
+        w = J.no_mis ? 1.f : (float)(1.0 / winv);
         if (!(w >= 0.f)) w = 0.f;
         ill = contrib * w;
         float* px = J.acc_eye + 3 * (size_t)pix_own;
@@ -342,15 +343,34 @@ __device__ inline void connect_strategies(const Job& J, const int si, const int 
       if (norm(contrib) > BDPT_EPS_F) {
         // ---- MIS weight (bidirection.cpp:121-293 in closed form, see header)
         double winv = 1.0;
+        const f3 woL = s >= 2 ? frL.to_local(Lv.wo) : zero;
         if (t >= 2) {
-          float P_le = s == 1 ? ls_dir_pdf : bsdf_pdf(ML, zero, cL) * Lv.q;
+          float P_le = s == 1 ? ls_dir_pdf : bsdf_pdf_mis(ML, woL, cL) * Lv.q;
           float r_t = P_le * g / E.D;
-          winv += (double)r_t * (double)r_t * (double)E.S;
+          float S_t = E.S;
+          if (ME.type == BDPT_MAT_MICROFACET && t >= 3) {
+            // wo-dependent density: the chain factor next to the connection cannot come from the walk's cache
+            Vtx P = V.get(0, t - 1);
+            f3 wv = P.pos - E.pos; float d2 = dot(wv, wv);
+            float gp = fabsf(woE.z * dot(wv * rsqrtf(d2), P.n)) / d2;
+            float R = bsdf_pdf_mis(ME, cE, woE) * E.q * gp / P.D;
+            S_t = clampS((type_is_delta(mat_type(sc, P.mat)) ? 0.f : 1.f) + (P.S > 0.f ? R * R * P.S : 0.f));
+          }
+          winv += (double)r_t * (double)r_t * (double)S_t;
         }
         if (s >= 2) {
-          float P_el = t == 1 ? cam_dir_pdf : bsdf_pdf(ME, zero, cE) * E.q;
+          float P_el = t == 1 ? cam_dir_pdf : bsdf_pdf_mis(ME, woE, cE) * E.q;
           float r_s = P_el * g / Lv.D;
-          winv += (double)r_s * (double)r_s * (double)Lv.S;
+          float S_s = Lv.S;
+          if (ML.type == BDPT_MAT_MICROFACET) {
+            Vtx P = V.get(1, s - 1);   // s - 1 == 1: the light origin record holds D = p_A, S = 1
+            f3 wv = P.pos - Lv.pos; float d2 = dot(wv, wv);
+            float gp = fabsf(woL.z * dot(wv * rsqrtf(d2), P.n)) / d2;
+            float R = bsdf_pdf_mis(ML, cL, woL) * Lv.q * gp / P.D;
+            bool dprev = s - 1 >= 2 && type_is_delta(mat_type(sc, P.mat));
+            S_s = clampS((dprev ? 0.f : 1.f) + (P.S > 0.f ? R * R * P.S : 0.f));
+          }
+          winv += (double)r_s * (double)r_s * (double)S_s;
         } else {
           // s == 1: the chain is evaluated at the ORIGINAL light-subpath origin
           float4 a, b;   // light_path[1]
@@ -360,12 +380,12 @@ __device__ inline void connect_strategies(const Job& J, const int si, const int 
           f3 wd = wv * rsqrtf(d2);
           float cosA, P_el;
           if (t == 1) { cosA = dot(ve_n, wd); P_el = cam_dir_pdf; }
-          else { f3 wl = frE.to_local(wd); cosA = wl.z; P_el = bsdf_pdf(ME, zero, wl) * E.q; }
+          else { f3 wl = frE.to_local(wd); cosA = wl.z; P_el = bsdf_pdf_mis(ME, woE, wl) * E.q; }
           float gp = fabsf(cosA * dot(wd, mk3(b.x, b.y, b.z))) / d2;
           float r_s = P_el * gp / b.w;
           winv += (double)r_s * (double)r_s;
         }
-        w = (float)(1.0 / winv);
+        w = J.no_mis ? 1.f : (float)(1.0 / winv);
         if (!(w >= 0.f)) w = 0.f;  // NaN guard
         ill = contrib * w;
         push = w > 0.f;
@@ -574,7 +594,7 @@ __device__ inline bool walk_shade(const Job& J, WalkState& W, Trav& T) {
   const bool delta_j = type_is_delta(M.type);
   const float D_j = (W.kind == 0 && W.j == 2) ? 1.f : W.pdfeval_prev * g;
   const f3 zero = mk3(0.f);
-  const float D_rev = bsdf_pdf(M, zero, w_out) * p_keep * g;
+  const float D_rev = bsdf_pdf_mis(M, wi, w_out) * p_keep * g;
   float S_j = (delta_j || W.delta_prev) ? 0.f : 1.f;
   if (W.S_prev > 0.f) { float R = D_rev / W.D_prev; S_j += R * R * W.S_prev; }
   S_j = clampS(S_j);
@@ -589,7 +609,7 @@ __device__ inline bool walk_shade(const Job& J, WalkState& W, Trav& T) {
   if (J.roulette && !(W.rng.uniform() < p_keep)) return false;
   if (is_zero(f)) return false;
 
-  W.pdfeval_prev = bsdf_pdf(M, zero, wi) * p_keep;
+  W.pdfeval_prev = bsdf_pdf_mis(M, w_out, wi) * p_keep;
   W.prev_f = f; W.prev_n = n; W.prev_pdf = pdf * p_keep;
   W.D_prev = D_j; W.S_prev = S_j; W.delta_prev = delta_j;
   W.j++;

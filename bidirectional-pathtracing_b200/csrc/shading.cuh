@@ -152,6 +152,14 @@ __device__ inline float bsdf_pdf(const Mat& m, f3 wo, f3 wi) {
   return 0.f;
 }
 
+// The density the MIS chains use for "scatter toward wi at this vertex".  The reference always passes
+// wo = (0,0,0) (bidirection.cpp:150,241), which is replicated for every BSDF it can evaluate that
+// way.  Its MicrofacetBSDF::sample_pdf aborts instead (advanced_bsdf.cpp:144-148), so for microfacet — an
+// extension with no reference behaviour to match — the real arrival direction wo is used.
+__device__ inline float bsdf_pdf_mis(const Mat& m, f3 wo_real, f3 wi) {
+  return bsdf_pdf(m, m.type == BDPT_MAT_MICROFACET ? wo_real : mk3(0.f), wi);
+}
+
 // BSDF::sample_f(wo, &wi, &pdf): bsdf.cpp:65-74 diffuse; :106-110 emission;
 // advanced_bsdf.cpp:21-29 mirror; :163-175 refraction; :198-234 glass; :97-141 microfacet.
 // Draw order follows the reference: two uniforms for a hemisphere sample (Xi1 then Xi2), one coin

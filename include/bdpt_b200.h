@@ -45,7 +45,8 @@ enum BdptBuffer {
 };
 
 enum BdptRenderFlags {
-  BDPT_FLAG_ROULETTE = 1  /* enable the rule the reference ships commented out (bidirection.cpp:87-93) */
+  BDPT_FLAG_ROULETTE = 1, /* enable the rule the reference ships commented out (bidirection.cpp:87-93) */
+  BDPT_FLAG_NO_MIS = 2    /* test hook: every strategy weighted 1, the reference's "no MIS" switch (bidirection.cpp:124-126) */
 };
 
 typedef struct BdptRenderParams {

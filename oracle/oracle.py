@@ -105,13 +105,13 @@ class Oracle:
     def camera_eval(self, q):
         return self._batch("oracle_camera_eval", q, 5, 11)
 
-    def render(self, ns: int, m: int, *, roulette: int = 0, rng_mode: int = 1, seed: int = 0, first_sample: int = 0,
+    def render(self, ns: int, m: int, *, roulette: int = 0, no_mis: int = 0, rng_mode: int = 1, seed: int = 0, first_sample: int = 0,
                n_samples: int | None = None, threads: int = 1, strategy: tuple[int, int] | None = None):
         """Returns (sum, eye, light) as (H, W, 3) fp64 arrays (row 0 = bottom) and the ray count."""
         n_samples = ns if n_samples is None else n_samples
         bufs = [np.zeros((self.H, self.W, 3), np.float64) for _ in range(3)]
         t, s = strategy if strategy else (-1, -1)
-        rays = lib().oracle_render(self.h, ns, m, roulette, rng_mode, seed, first_sample, n_samples, threads, t, s,
+        rays = lib().oracle_render(self.h, ns, m, (1 if roulette else 0) | (2 if no_mis else 0), rng_mode, seed, first_sample, n_samples, threads, t, s,
                                    _dp(bufs[0]), _dp(bufs[1]), _dp(bufs[2]))
         return bufs[0], bufs[1], bufs[2], int(rays)
 

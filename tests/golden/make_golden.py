@@ -41,6 +41,11 @@ SCENES = {
 }
 
 
+# scenes the reference cannot render with BDPT (MicrofacetBSDF::sample_pdf aborts, advanced_bsdf.cpp:144-148;
+# RefractionBSDF::sample_f leaves its outputs unset on total internal reflection, :166-168): only the scene dump
+EXTRA_SCENES = ["CBspheres_microfacet_al_ag", "CBspheres_refract"]
+
+
 def unit(v):
     return v / np.linalg.norm(v, axis=-1, keepdims=True)
 
@@ -65,6 +70,11 @@ def main():
     only = sys.argv[1] if len(sys.argv) > 1 else "all"
     assert O.have_ref(), "build the reference first: make -C oracle ref"
     os.makedirs(os.path.join(OUT, "scenes"), exist_ok=True)
+    for name in EXTRA_SCENES:
+        tmp = os.path.join(OUT, "scenes", name + ".fscene")
+        O.ref_dump(O.ref_scene(name), tmp)
+        fs.load(tmp).save(tmp + ".gz")
+        os.remove(tmp)
     for name, (W, H, ns, m) in SCENES.items():
         dae = O.ref_scene(name)
         tmp = os.path.join(OUT, "scenes", name + ".fscene")
