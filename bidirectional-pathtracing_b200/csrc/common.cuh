@@ -29,7 +29,8 @@ __host__ __device__ inline f3 cross(f3 u, f3 v) {
 }
 __device__ inline float norm2(f3 a) { return dot(a, a); }
 __device__ inline float norm(f3 a) { return sqrtf(dot(a, a)); }
-__device__ inline f3 normalized(f3 a) { return a * (1.0f / sqrtf(dot(a, a))); }
+// rsqrtf (MUFU.RSQ, <= 2 ulp): the IEEE sqrt + divide form was ~10 % of k_connect's issued instructions
+__device__ inline f3 normalized(f3 a) { return a * rsqrtf(dot(a, a)); }
 __device__ inline bool is_zero(f3 a) { return a.x == 0.f && a.y == 0.f && a.z == 0.f; }
 
 // Orthonormal frame around a normal; same axis choice as the reference's make_coord_space

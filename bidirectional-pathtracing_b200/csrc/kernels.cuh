@@ -239,17 +239,17 @@ __device__ inline void connect_strategies(const Job& J, const int si, const int 
   const DScene& sc = J.sc;
   const f3 zero = mk3(0.f);
 
-  Vtx E; Mat ME; Frame frE;
+  Vtx E; Mat ME;
   E.mat = -1; E.D = 1.f; E.S = 0.f; E.q = 1.f;
   if (t >= 2) {
     E = V.get(0, t);
     ME = load_mat(sc, E.mat);
-    frE = make_frame(E.n);
   } else {
     E.pos = J.cam.pos; E.alpha = mk3(1.f); E.n = zero; E.wo = zero;
     ME.type = -1;
   }
-  const f3 woE = t >= 2 ? frE.to_local(E.wo) : zero;
+  // local z of the direction back along the eye subpath (every BSDF here needs only z's and one dot product)
+  const float woEz = t >= 2 ? dot(E.n, E.wo) : 0.f;
   const unsigned int pix_own = (unsigned int)(y * J.cam.W + x);
   unsigned int nconn = 0;
 
@@ -285,7 +285,7 @@ __device__ inline void connect_strategies(const Job& J, const int si, const int 
             light_sample_pdf(L, E.pos, -E.wo, &pp, &dp);  // dir pdf of leaving the light toward e_{t-1}
             f3 wv = P.pos - E.pos; float d2 = dot(wv, wv);
             f3 wd = wv * rsqrtf(d2);
-            float gp = fabsf(dot(frE.z, wd) * dot(wd, P.n)) / d2;
+            float gp = fabsf(dot(E.n, wd) * dot(wd, P.n)) / d2;
             float Rp = dp * gp / P.D;
             tail = Rp * Rp * P.S;
           }
@@ -299,7 +299,7 @@ __device__ inline void connect_strategies(const Job& J, const int si, const int 
       }
     } else {
       // ---- light-side endpoint vl
-      Vtx Lv; Mat ML; Frame frL;
+      Vtx Lv; Mat ML;
       float ls_dir_pdf = 0.f;
       if (s == 1) {
         // fresh light point for this t (bidirection.cpp:332-358)
@@ -317,7 +317,6 @@ __device__ inline void connect_strategies(const Job& J, const int si, const int 
         Lv = V.get(1, s);
         ML = load_mat(sc, Lv.mat);
       }
-      if (s >= 2) frL = make_frame(Lv.n);
       // ---- eye-side endpoint ve (t == 1: the pinhole, bidirection.cpp:360-383)
       f3 ve_pos = E.pos, ve_n = E.n, eye_alpha = E.alpha;
       float cam_dir_pdf = 0.f;
@@ -331,42 +330,46 @@ __device__ inline void connect_strategies(const Job& J, const int si, const int 
       const float dist2 = dot(cv, cv);
       const float dist = sqrtf(dist2);
       const f3 cdir = cv * (1.0f / dist);
+      // local z's of the connection at both ends, and the dot products with the directions back along the subpaths
+      const float cEz = dot(ve_n, cdir);               // t == 1: ve_n = cdir direction -> 1
+      const float cLz = -dot(Lv.n, cdir);
+      const float woLz = s >= 2 ? dot(Lv.n, Lv.wo) : 0.f;
+      const float dotE = t >= 2 ? dot(E.wo, cdir) : 0.f;
+      const float dotL = s >= 2 ? -dot(Lv.wo, cdir) : 0.f;
       // bsdf->f at both ends (bidirection.cpp:385-416)
       f3 f_eye = mk3(1.f), f_light = mk3(1.f);
-      f3 cE = zero, cL = zero;
-      if (t >= 2) { cE = frE.to_local(cdir); f_eye = bsdf_f(ME, woE, cE); }
-      if (s >= 2) { cL = frL.to_local(-cdir); f_light = bsdf_f(ML, cL, frL.to_local(Lv.wo)); }
-      const float g = fabsf(dot(Lv.n, cdir) * dot(ve_n, cdir)) / dist2;
+      if (t >= 2) f_eye = bsdf_f_z(ME, woEz, cEz, dotE);
+      if (s >= 2) f_light = bsdf_f_z(ML, cLz, woLz, dotL);
+      const float g = fabsf(cLz * cEz) / dist2;
       contrib = eye_alpha * Lv.alpha * (f_eye * f_light) * g;
       bool push = false;
       unsigned int target = pix_own;
       if (norm(contrib) > BDPT_EPS_F) {
         // ---- MIS weight (bidirection.cpp:121-293 in closed form, see header)
         double winv = 1.0;
-        const f3 woL = s >= 2 ? frL.to_local(Lv.wo) : zero;
         if (t >= 2) {
-          float P_le = s == 1 ? ls_dir_pdf : bsdf_pdf_mis(ML, woL, cL) * Lv.q;
+          float P_le = s == 1 ? ls_dir_pdf : bsdf_pdf_mis_z(ML, woLz, cLz, dotL) * Lv.q;
           float r_t = P_le * g / E.D;
           float S_t = E.S;
           if (ME.type == BDPT_MAT_MICROFACET && t >= 3) {
             // wo-dependent density: the chain factor next to the connection cannot come from the walk's cache
             Vtx P = V.get(0, t - 1);
             f3 wv = P.pos - E.pos; float d2 = dot(wv, wv);
-            float gp = fabsf(woE.z * dot(wv * rsqrtf(d2), P.n)) / d2;
-            float R = bsdf_pdf_mis(ME, cE, woE) * E.q * gp / P.D;
+            float gp = fabsf(woEz * dot(wv * rsqrtf(d2), P.n)) / d2;
+            float R = bsdf_pdf_mis_z(ME, cEz, woEz, dotE) * E.q * gp / P.D;
             S_t = clampS((type_is_delta(mat_type(sc, P.mat)) ? 0.f : 1.f) + (P.S > 0.f ? R * R * P.S : 0.f));
           }
           winv += (double)r_t * (double)r_t * (double)S_t;
         }
         if (s >= 2) {
-          float P_el = t == 1 ? cam_dir_pdf : bsdf_pdf_mis(ME, woE, cE) * E.q;
+          float P_el = t == 1 ? cam_dir_pdf : bsdf_pdf_mis_z(ME, woEz, cEz, dotE) * E.q;
           float r_s = P_el * g / Lv.D;
           float S_s = Lv.S;
           if (ML.type == BDPT_MAT_MICROFACET) {
             Vtx P = V.get(1, s - 1);   // s - 1 == 1: the light origin record holds D = p_A, S = 1
             f3 wv = P.pos - Lv.pos; float d2 = dot(wv, wv);
-            float gp = fabsf(woL.z * dot(wv * rsqrtf(d2), P.n)) / d2;
-            float R = bsdf_pdf_mis(ML, cL, woL) * Lv.q * gp / P.D;
+            float gp = fabsf(woLz * dot(wv * rsqrtf(d2), P.n)) / d2;
+            float R = bsdf_pdf_mis_z(ML, cLz, woLz, dotL) * Lv.q * gp / P.D;
             bool dprev = s - 1 >= 2 && type_is_delta(mat_type(sc, P.mat));
             S_s = clampS((dprev ? 0.f : 1.f) + (P.S > 0.f ? R * R * P.S : 0.f));
           }
@@ -378,9 +381,8 @@ __device__ inline void connect_strategies(const Job& J, const int si, const int 
           f3 wv = mk3(a.x, a.y, a.z) - ve_pos;
           float d2 = dot(wv, wv);
           f3 wd = wv * rsqrtf(d2);
-          float cosA, P_el;
-          if (t == 1) { cosA = dot(ve_n, wd); P_el = cam_dir_pdf; }
-          else { f3 wl = frE.to_local(wd); cosA = wl.z; P_el = bsdf_pdf_mis(ME, woE, wl) * E.q; }
+          const float cosA = dot(ve_n, wd);
+          const float P_el = t == 1 ? cam_dir_pdf : bsdf_pdf_mis_z(ME, woEz, cosA, dot(E.wo, wd)) * E.q;
           float gp = fabsf(cosA * dot(wd, mk3(b.x, b.y, b.z))) / d2;
           float r_s = P_el * gp / b.w;
           winv += (double)r_s * (double)r_s;

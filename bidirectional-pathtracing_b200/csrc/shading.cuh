@@ -90,8 +90,7 @@ __device__ inline float mf_D(float alpha, float hz) {
   float tan2 = (1.f - c2) / c2;
   return expf(-tan2 / (alpha * alpha)) / (BDPT_PI * alpha * alpha * c2 * c2);
 }
-__device__ inline f3 mf_F(const Mat& m, f3 wi) {
-  float c = fabsf(wi.z) / norm(wi);
+__device__ inline f3 mf_F(const Mat& m, float c) {  // c = |cos theta_i|
   float c2 = c * c;
   f3 e2k2 = m.eta * m.eta + m.k * m.k;
   f3 tec = 2.f * c * m.eta;
@@ -105,59 +104,81 @@ __device__ inline f3 mf_F(const Mat& m, f3 wi) {
   return (rs + rp) * 0.5f;
 }
 
+// The BSDF evaluations below only ever need the z components of the two local directions and their dot
+// product (every lobe here is isotropic about the shading normal), so they are written in that form:
+// k_connect then needs no tangent frame at all — woz = dot(n, wo_world), wiz = dot(n, wi_world) — and the
+// vector forms used by the walk and the test hooks forward to them.  Directions are unit length.
+
+// Schlick term from the cosine of the refracted direction
+__device__ inline float glass_R_cos(float ior, float c, bool wo_z_positive) {
+  float eta = wo_z_positive ? 1.0f / ior : ior;
+  float r0 = (1.f - eta) / (1.f + eta);
+  r0 *= r0;
+  return r0 + (1.f - r0) * pow5(1.f - c);
+}
+
 // BSDF::f(wo, wi): bsdf.cpp:52-60 diffuse; :99-101 emission; advanced_bsdf.cpp:17-19,
 // :159-161,:194-196 mirror/refraction/glass (all zero); :84-95 microfacet.
-__device__ inline f3 bsdf_f(const Mat& m, f3 wo, f3 wi) {
+__device__ inline f3 bsdf_f_z(const Mat& m, float woz, float wiz, float dot_wowi) {
   if (m.type == BDPT_MAT_DIFFUSE) {
-    if (wo.z < 0.f || wi.z < 0.f) return mk3(0.f);
+    if (woz < 0.f || wiz < 0.f) return mk3(0.f);
     return m.reflectance * BDPT_INV_PI;
   }
   if (m.type == BDPT_MAT_MICROFACET) {
-    if (wo.z <= BDPT_EPS_F || wi.z <= BDPT_EPS_F) return mk3(0.f);
-    f3 h = normalized(wo + wi);
-    float G = 1.0f / (1.0f + mf_lambda(m.alpha, wi.z) + mf_lambda(m.alpha, wo.z));
-    return mf_F(m, wi) * (G * mf_D(m.alpha, h.z) / (4.f * wo.z * wi.z));
+    if (woz <= BDPT_EPS_F || wiz <= BDPT_EPS_F) return mk3(0.f);
+    float hz = (woz + wiz) * rsqrtf(fmaxf(2.f + 2.f * dot_wowi, 1e-20f));   // z of normalize(wo + wi)
+    float G = 1.0f / (1.0f + mf_lambda(m.alpha, wiz) + mf_lambda(m.alpha, woz));
+    return mf_F(m, fabsf(wiz)) * (G * mf_D(m.alpha, hz) / (4.f * woz * wiz));
   }
   return mk3(0.f);
 }
+__device__ inline f3 bsdf_f(const Mat& m, f3 wo, f3 wi) { return bsdf_f_z(m, wo.z, wi.z, dot(wo, wi)); }
 
 // BSDF::sample_pdf(wo, wi): bsdf.cpp:76-81,112-117; advanced_bsdf.cpp:31-34,180-183,236-259.
-// The reference's MIS always passes wo = (0,0,0) (bidirection.cpp:150,241): callers here pass
-// wo_z = 0 for that.  Microfacet: the reference aborts (advanced_bsdf.cpp:144-148); here it
-// returns the half-vector density sample_f uses (needs the real wo).
-__device__ inline float bsdf_pdf(const Mat& m, f3 wo, f3 wi) {
+// Microfacet: the reference aborts (advanced_bsdf.cpp:144-148); here it returns the half-vector density
+// sample_f uses (needs the real wo).
+__device__ inline float bsdf_pdf_z(const Mat& m, float woz, float wiz, float dot_wowi) {
   switch (m.type) {
     case BDPT_MAT_DIFFUSE:
     case BDPT_MAT_EMISSION:
-      return cosine_pdf(wi.z);
+      return cosine_pdf(wiz);
     case BDPT_MAT_MIRROR:
     case BDPT_MAT_REFRACTION:
       return 1.f;
     case BDPT_MAT_GLASS: {
-      f3 refr;
-      if (!refract_local(wi, &refr, m.ior)) return 1.f;
-      float R = glass_R(m.ior, refr, wo.z > 0.f);
-      return wi.z > 0.f ? R : 1.f - R;
+      // refract(wi) then Schlick on the refracted cosine: only |refr.z| / |refr| is needed
+      float eta = wiz > 0.f ? 1.0f / m.ior : m.ior;
+      float s2 = eta * eta * (1.f - wiz * wiz);
+      float z_sq = 1.f - s2;
+      if (z_sq < 0.f) return 1.f;
+      float R = glass_R_cos(m.ior, sqrtf(z_sq) * rsqrtf(s2 + z_sq), woz > 0.f);
+      return wiz > 0.f ? R : 1.f - R;
     }
     case BDPT_MAT_MICROFACET: {
-      if (wo.z <= BDPT_EPS_F || wi.z <= BDPT_EPS_F) return 0.f;
-      f3 h = normalized(wo + wi);
-      float c2 = h.z * h.z;
+      if (woz <= BDPT_EPS_F || wiz <= BDPT_EPS_F) return 0.f;
+      float il = rsqrtf(fmaxf(2.f + 2.f * dot_wowi, 1e-20f));
+      float hz = (woz + wiz) * il;
+      float c2 = hz * hz;
       float tan2 = (1.f - c2) / c2;
       // p_theta * p_phi / sin(theta) of advanced_bsdf.cpp:126-130
-      float pdf_h = 2.f * expf(-tan2 / (m.alpha * m.alpha)) / (m.alpha * m.alpha * c2 * h.z) * (0.5f * BDPT_INV_PI);
-      return pdf_h / (4.f * dot(wi, h));
+      float pdf_h = 2.f * expf(-tan2 / (m.alpha * m.alpha)) / (m.alpha * m.alpha * c2 * hz) * (0.5f * BDPT_INV_PI);
+      return pdf_h / (4.f * (dot_wowi + 1.f) * il);   // dot(wi, h)
     }
   }
   return 0.f;
 }
+__device__ inline float bsdf_pdf(const Mat& m, f3 wo, f3 wi) { return bsdf_pdf_z(m, wo.z, wi.z, dot(wo, wi)); }
 
 // The density the MIS chains use for "scatter toward wi at this vertex".  The reference always passes
 // wo = (0,0,0) (bidirection.cpp:150,241), which is replicated for every BSDF it can evaluate that
 // way.  Its MicrofacetBSDF::sample_pdf aborts instead (advanced_bsdf.cpp:144-148), so for microfacet — an
 // extension with no reference behaviour to match — the real arrival direction wo is used.
+__device__ inline float bsdf_pdf_mis_z(const Mat& m, float woz_real, float wiz, float dot_wowi) {
+  const bool mf = m.type == BDPT_MAT_MICROFACET;
+  return bsdf_pdf_z(m, mf ? woz_real : 0.f, wiz, mf ? dot_wowi : 0.f);
+}
 __device__ inline float bsdf_pdf_mis(const Mat& m, f3 wo_real, f3 wi) {
-  return bsdf_pdf(m, m.type == BDPT_MAT_MICROFACET ? wo_real : mk3(0.f), wi);
+  return bsdf_pdf_mis_z(m, wo_real.z, wi.z, dot(wo_real, wi));
 }
 
 // BSDF::sample_f(wo, &wi, &pdf): bsdf.cpp:65-74 diffuse; :106-110 emission;
