@@ -64,6 +64,7 @@ struct BdptContext {
   // BVH size at upload (tiny trees have no traversal divergence to hide).  Override: BDPT_SCHED.
   int sched = -1, sched_req = -1;
   int variant = 1;      // scheduling-threshold variant of k_walk_pt (BDPT_VARIANT, tuning only)
+  int top_nodes = 73;   // BVH nodes staged in shared memory: root + 8 + 64 = the top three levels (BDPT_TOP_NODES)
   int connect_minb = 6; // __launch_bounds__ min blocks of k_connect (BDPT_CONNECT_MINB, tuning only)
   int batch_log2 = 22, batch_gib = 12;  // batch size cap (samples) and its memory budget (BDPT_BATCH_LOG2, BDPT_BATCH_GIB)
   int walk_ctas = 4, shadow_ctas = 8;  // resident CTAs per SM of the persistent kernels
@@ -195,6 +196,7 @@ void fill_job(BdptContext* ctx, const BdptRenderParams* p, Job* J) {
   J->npix_pad = J->tiles_x * ((ctx->H + 3) / 4) * 32;
   J->roulette = (p->flags & BDPT_FLAG_ROULETTE) ? 1 : 0;
   J->no_mis = (p->flags & BDPT_FLAG_NO_MIS) ? 1 : 0;
+  J->ntop = std::min(ctx->top_nodes, ctx->sc.n_nodes);
   J->only_t = p->only_t; J->only_s = p->only_s;
   J->single_x = -1; J->single_y = -1;
 }
@@ -222,12 +224,12 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
   } else if (ctx->sched) {
     const int g = ctx->sm_count * ctx->walk_ctas;
     switch (ctx->variant) {
-      case 1: k_walk_pt<16, 8><<<g, threads, 0, ctx->stream>>>(J); break;
-      case 2: k_walk_pt<20, 8><<<g, threads, 0, ctx->stream>>>(J); break;
-      case 3: k_walk_pt<12, 4><<<g, threads, 0, ctx->stream>>>(J); break;
-      case 4: k_walk_pt<16, 16><<<g, threads, 0, ctx->stream>>>(J); break;
-      case 5: k_walk_pt<8, 8><<<g, threads, 0, ctx->stream>>>(J); break;
-      default: k_walk_pt<12, 8><<<g, threads, 0, ctx->stream>>>(J); break;
+      case 1: k_walk_pt<16, 8><<<g, threads, (size_t)J.ntop * 80, ctx->stream>>>(J); break;
+      case 2: k_walk_pt<20, 8><<<g, threads, (size_t)J.ntop * 80, ctx->stream>>>(J); break;
+      case 3: k_walk_pt<12, 4><<<g, threads, (size_t)J.ntop * 80, ctx->stream>>>(J); break;
+      case 4: k_walk_pt<16, 16><<<g, threads, (size_t)J.ntop * 80, ctx->stream>>>(J); break;
+      case 5: k_walk_pt<8, 8><<<g, threads, (size_t)J.ntop * 80, ctx->stream>>>(J); break;
+      default: k_walk_pt<12, 8><<<g, threads, (size_t)J.ntop * 80, ctx->stream>>>(J); break;
     }
   }
   else k_walk<<<(2 * J.B + threads - 1) / threads, threads, 0, ctx->stream>>>(J);
@@ -240,7 +242,7 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
     default: k_connect<TRACE, 3><<<cgrid, threads, 0, ctx->stream>>>(J); break;
   }
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 2), ctx->stream);
-  if (ctx->sched) k_shadow_pt<<<ctx->sm_count * ctx->shadow_ctas, threads, 0, ctx->stream>>>(J);
+  if (ctx->sched) k_shadow_pt<<<ctx->sm_count * ctx->shadow_ctas, threads, (size_t)J.ntop * 80, ctx->stream>>>(J);
   else k_shadow<<<ctx->sm_count * 8, threads, 0, ctx->stream>>>(J);
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 3), ctx->stream);
   ctx->stats.kernel_launches += 3;
@@ -302,6 +304,7 @@ int bdpt_create(int device, BdptContext** out) {
   ctx->sched = ctx->sched_req >= 0 ? ctx->sched_req : 1;
   if (const char* e = getenv("BDPT_BATCH_LOG2")) ctx->batch_log2 = std::min(24, std::max(10, atoi(e)));
   if (const char* e = getenv("BDPT_BATCH_GIB")) ctx->batch_gib = std::min(64, std::max(1, atoi(e)));
+  if (const char* e = getenv("BDPT_TOP_NODES")) ctx->top_nodes = std::max(0, std::min(512, atoi(e)));
   if (const char* e = getenv("BDPT_CONNECT_MINB")) ctx->connect_minb = atoi(e);
   if (const char* e = getenv("BDPT_VARIANT")) ctx->variant = atoi(e);
   if (const char* e = getenv("BDPT_WALK_CTAS")) ctx->walk_ctas = std::max(1, atoi(e));

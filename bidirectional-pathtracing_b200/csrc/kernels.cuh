@@ -53,6 +53,7 @@ struct Job {
   int first_sample;           // sample index of job-sample 0
   int tiles_x, npix_pad;      // 8x4 pixel tiles per row; padded pixel count
   int roulette;
+  int ntop;                   // BVH nodes staged in shared memory by the persistent kernels
   int no_mis;                 // weight 1 for every strategy: the reference's own debug switch (bidirection.cpp:124-126)
   int only_t, only_s;
   int single_x, single_y;     // >= 0: the job is this one pixel (trace mode)
@@ -76,7 +77,6 @@ __device__ inline bool decode_sample(const Job& J, unsigned long long g, int* x,
 
 #define VSLOT(J, kind, j, i) ((size_t)((kind) * ((J).m + 1) + ((j)-1)) * (size_t)(J).B + (size_t)(i))
 
-__device__ inline float sqr(float x) { return x * x; }
 __device__ inline float clampS(float s) { return fminf(s, 1e30f); }
 
 // ---------------------------------------------------------------------------------------- walk
@@ -488,7 +488,15 @@ __device__ inline unsigned warp_fetch(unsigned* cursor, unsigned total, unsigned
   return got ? my : BDPT_NONE;
 }
 
+// Copies the first `ntop` BVH nodes (the upper levels: nodes are stored breadth first) into shared memory.
+__device__ inline void stage_top_nodes(const Job& J, uint4* top) {
+  for (int i = threadIdx.x; i < J.ntop * 5; i += blockDim.x) top[i] = J.sc.nodes[i];
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(128) k_shadow_pt(const Job J) {
+  extern __shared__ uint4 top[];
+  stage_top_nodes(J, top);
   const unsigned n = min(J.qctr[0], J.qcap);
   Trav T;
   uint2 stack[BDPT_STACK];
@@ -510,7 +518,7 @@ __global__ void __launch_bounds__(128) k_shadow_pt(const Job J) {
       if (wf.exhausted) break;
       continue;
     }
-    if (active && T.step<true>(J.sc, stack)) {
+    if (active && T.step<true>(J.sc, stack, top, (uint32_t)J.ntop)) {
       traced++;
       active = false;
       if (T.hit.leaf < 0) {
@@ -622,6 +630,8 @@ __device__ inline bool walk_shade(const Job& J, WalkState& W, Trav& T) {
 // phase: 0 = empty (wants a subpath), 1 = traversing, 2 = traversal finished (wants shading)
 template <int SHADE_THRESHOLD, int FETCH_THRESHOLD>
 __global__ void __launch_bounds__(128) k_walk_pt(const Job J) {
+  extern __shared__ uint4 top[];
+  stage_top_nodes(J, top);
   Trav T;
   uint2 stack[BDPT_STACK];
   WalkState W;
@@ -648,7 +658,7 @@ __global__ void __launch_bounds__(128) k_walk_pt(const Job J) {
     }
     if (__ballot_sync(0xffffffffu, phase != 0) == 0u && wf.exhausted) break;
     if (phase == 1) {
-      if (T.step<false>(J.sc, stack)) { phase = 2; nrays++; }
+      if (T.step<false>(J.sc, stack, top, (uint32_t)J.ntop)) { phase = 2; nrays++; }
     }
   }
   unsigned int tot = __reduce_add_sync(0xffffffffu, nrays);

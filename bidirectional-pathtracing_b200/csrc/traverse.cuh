@@ -86,8 +86,10 @@ struct Trav {
 
   // `stack` is the caller's per-thread array of BDPT_STACK entries (kept out of this struct so that the
   // scalar state stays in registers)
+  // `top` (optional): the first `ntop` nodes of the tree — its upper levels, the builder emits nodes breadth
+  // first — staged in shared memory by the calling kernel.
   template <bool ANY_HIT>
-  __device__ inline bool step(const DScene& sc, uint2* stack) {
+  __device__ inline bool step(const DScene& sc, uint2* stack, const uint4* top = nullptr, const uint32_t ntop = 0) {
     const uint32_t octinv = oct ^ 7u;
     // ---- pop the nearest internal child of the current group
     uint32_t bit = 31u - (uint32_t)__clz(group.y);
@@ -97,8 +99,15 @@ struct Trav {
     if (group.y > 0x00ffffffu) stack[sp++] = group;
     uint32_t slot = (bit - 24u) ^ octinv;
     uint32_t rel = __popc(imask_prev & ((1u << slot) - 1u));
-    const uint4* np = sc.nodes + (size_t)(base + rel) * 5;
-    uint4 q0 = ldg4(np), q1 = ldg4(np + 1), q2 = ldg4(np + 2), q3 = ldg4(np + 3), q4 = ldg4(np + 4);
+    const uint32_t ni = base + rel;
+    uint4 q0, q1, q2, q3, q4;
+    if (ni < ntop) {
+      const uint4* np = top + (size_t)ni * 5;
+      q0 = np[0]; q1 = np[1]; q2 = np[2]; q3 = np[3]; q4 = np[4];
+    } else {
+      const uint4* np = sc.nodes + (size_t)ni * 5;
+      q0 = ldg4(np); q1 = ldg4(np + 1); q2 = ldg4(np + 2); q3 = ldg4(np + 3); q4 = ldg4(np + 4);
+    }
 
     f3 adj, org;
     adj.x = __uint_as_float((q0.w & 0xffu) << 23) * idir.x;

@@ -87,7 +87,6 @@ inline V4 v4(V3 v, double w) { return V4{v.x, v.y, v.z, w}; }
 enum class Kind { NONE, CAMERA, LIGHT, SPHERE, POLYMESH };
 enum class LightKind { NONE, AMBIENT, DIRECTIONAL, AREA, POINT, SPOT };
 
-struct MaterialDesc { BdptMaterial m; };
 struct NodeDesc {
   Kind kind = Kind::NONE;
   M4 transform = M4::identity();

@@ -263,6 +263,22 @@ def test_config2_full_size_runs_and_tonemaps(api):
     assert np.mean(np.abs(png[..., :3].astype(np.int32) - exp.astype(np.int32)) <= 1) > 0.999
 
 
+def test_config3_shape_long_paths_with_roulette(api):
+    """configs[3]'s shape: CBgems at 1024x768, m=16, roulette (reduced spp): glass caustic paths, 17 x 18 strategies."""
+    R = make_renderer(api, "CBgems", 1024, 768, ns_aa=8, max_ray_depth=16, seed=3, roulette=True)
+    R.render()
+    s, e, l = (R.framebuffer(i) for i in range(3))
+    assert np.isfinite(s).all() and np.allclose(s, e + l, rtol=1e-5, atol=1e-6)
+    assert 0.2 < s.mean() < 0.8 and l.mean() > 0
+    st = R.stats()
+    assert st["samples"] == 1024 * 768 * 8 and st["rays_shadow"] > st["samples"]
+    # the same frame without roulette agrees in the mean (roulette is unbiased) and traces more rays
+    R2 = make_renderer(api, "CBgems", 1024, 768, ns_aa=8, max_ray_depth=16, seed=4)
+    R2.render()
+    assert abs(R2.framebuffer(0).mean() - s.mean()) <= 1e-2 * s.mean()
+    assert R2.stats()["rays_closest"] > st["rays_closest"]
+
+
 def test_no_mis_switch_matches_oracle(api, O):
     """The reference's "no MIS" debug switch (bidirection.cpp:124-126): every strategy weighted 1."""
     name, W, H, ns, m = "CBspheres_lambertian", 48, 36, 8, 4
