@@ -15,6 +15,7 @@ Writes:
   <name>.render.npz         reference `-t 1` render (fp64 sum / eye / light buffers, ray count)
   CBspheres_lambertian.strategies.npz   reference per-(t,s) images (debug filter of bidirection.cpp:492-493)
   <name>.converged.npz      reference render at 1024 spp, 64x48, all host threads (statistical pin)
+  published_pooled.npz      the author's published 128-spp PNGs (assets/), box-filtered to 60x45
 """
 import os
 import sys
@@ -119,6 +120,15 @@ def main():
         np.savez_compressed(os.path.join(OUT, name + ".converged.npz"), sum=s.astype(np.float32), eye=e.astype(np.float32),
                             light=l.astype(np.float32), params=np.array([W, H, ns, m]))
         print(name, "converged", info)
+
+    # the author's PUBLISHED renders (assets/*_bdpt_128.png: 480x360, 128 spp, tone-mapped 8-bit) reduced to 60x45 box-filtered
+    # means: a loose pin that is independent of our build of the reference (framing, tone map, overall light transport)
+    from PIL import Image
+    pub = {}
+    for name in ("CBspheres", "CBgems"):
+        a = np.asarray(Image.open(f"/root/reference/assets/{name}_bdpt_128.png").convert("RGB")).astype(np.float64)
+        pub[name] = a.reshape(45, 8, 60, 8, 3).mean((1, 3)).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "published_pooled.npz"), **pub)
 
     # per-strategy images, small
     name, (W, H, ns, m) = "CBspheres_lambertian", (32, 24, 2, 3)

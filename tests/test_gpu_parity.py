@@ -292,6 +292,19 @@ def test_no_mis_switch_matches_oracle(api, O):
     assert got.mean() > 1.5 * W2.framebuffer(0).mean()      # unweighted strategies over-count
 
 
+@pytest.mark.parametrize("name", ["CBspheres", "CBgems"])
+def test_matches_the_authors_published_render(api, name):
+    """The 128-spp, 480x360 PNGs the author published (reference assets/*_bdpt_128.png), box-filtered to 60x45
+    (tests/golden/published_pooled.npz): same framing, tone map and light transport as the CUDA path at 128 spp."""
+    pub = np.load(os.path.join(GOLDEN, "published_pooled.npz"))[name].astype(np.float64)
+    R = make_renderer(api, name, 480, 360, ns_aa=128, max_ray_depth=5, seed=0)
+    R.render()
+    got = R.tonemap(0)[..., :3].astype(np.float64).reshape(45, 8, 60, 8, 3).mean((1, 3))
+    rmse = float(np.sqrt(np.mean((got - pub) ** 2)))
+    assert rmse <= 2.0, rmse            # 8-bit units
+    assert abs(got.mean() - pub.mean()) <= 1.0
+
+
 def test_roulette_is_unbiased(api):
     name, W, H, m = "CBspheres_lambertian", 48, 36, 6
     a = make_renderer(api, name, W, H, ns_aa=1024, max_ray_depth=m, seed=3); a.render()
