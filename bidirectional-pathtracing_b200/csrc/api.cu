@@ -63,14 +63,14 @@ struct BdptContext {
   // (measured slower: its state round-trips cost more HBM time than the divergence it removes); -1 = choose by
   // BVH size at upload (tiny trees have no traversal divergence to hide).  Override: BDPT_SCHED.
   int sched = -1, sched_req = -1;
-  int variant = 1;      // scheduling-threshold variant of k_walk_pt (BDPT_VARIANT, tuning only)
+  int variant = 0;      // k_walk_pt build: 0 = 6 CTAs/SM (default), 1 = 4 CTAs/SM without spills (BDPT_VARIANT, tuning only)
   // BVH nodes the persistent kernels stage in shared memory (BDPT_TOP_NODES; 73 = root + 8 + 64 = three levels).
   // Off by default: measured on B200 it changes nothing (-0.5 % at 73, -1.6 % at 300) — L1 already holds the top
   // of the tree (77 % L1 hit rate in k_walk_pt).
   int top_nodes = 0;
   int connect_minb = 6; // __launch_bounds__ min blocks of k_connect (BDPT_CONNECT_MINB, tuning only)
   int batch_log2 = 22, batch_gib = 12;  // batch size cap (samples) and its memory budget (BDPT_BATCH_LOG2, BDPT_BATCH_GIB)
-  int walk_ctas = 4, shadow_ctas = 8;  // resident CTAs per SM of the persistent kernels
+  int walk_ctas = 6, shadow_ctas = 8;  // resident CTAs per SM of the persistent kernels
 };
 
 namespace {
@@ -226,14 +226,11 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
     ctx->stats.kernel_launches += 2 * J.m;
   } else if (ctx->sched) {
     const int g = ctx->sm_count * ctx->walk_ctas;
-    switch (ctx->variant) {
-      case 1: k_walk_pt<16, 8><<<g, threads, (size_t)J.ntop * 80, ctx->stream>>>(J); break;
-      case 2: k_walk_pt<20, 8><<<g, threads, (size_t)J.ntop * 80, ctx->stream>>>(J); break;
-      case 3: k_walk_pt<12, 4><<<g, threads, (size_t)J.ntop * 80, ctx->stream>>>(J); break;
-      case 4: k_walk_pt<16, 16><<<g, threads, (size_t)J.ntop * 80, ctx->stream>>>(J); break;
-      case 5: k_walk_pt<8, 8><<<g, threads, (size_t)J.ntop * 80, ctx->stream>>>(J); break;
-      default: k_walk_pt<12, 8><<<g, threads, (size_t)J.ntop * 80, ctx->stream>>>(J); break;
-    }
+    // 6 CTAs/SM (80 registers, ~0.2 KB of spills) beats 4 CTAs at 101 registers by 6 %: the state machine is
+    // latency-bound between votes.  BDPT_VARIANT=1 selects the unspilled build for comparison.
+    if (ctx->variant == 1) k_walk_pt<16, 8, 4><<<g, threads, (size_t)J.ntop * 80, ctx->stream>>>(J);
+    else k_walk_pt<16, 8, 6><<<g, threads, (size_t)J.ntop * 80, ctx->stream>>>(J);
+  }
   }
   else k_walk<<<(2 * J.B + threads - 1) / threads, threads, 0, ctx->stream>>>(J);
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 1), ctx->stream);
@@ -245,7 +242,7 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
     default: k_connect<TRACE, 3><<<cgrid, threads, 0, ctx->stream>>>(J); break;
   }
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 2), ctx->stream);
-  if (ctx->sched) k_shadow_pt<<<ctx->sm_count * ctx->shadow_ctas, threads, (size_t)J.ntop * 80, ctx->stream>>>(J);
+  if (ctx->sched) k_shadow_pt<8><<<ctx->sm_count * ctx->shadow_ctas, threads, (size_t)J.ntop * 80, ctx->stream>>>(J);
   else k_shadow<<<ctx->sm_count * 8, threads, 0, ctx->stream>>>(J);
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 3), ctx->stream);
   ctx->stats.kernel_launches += 3;

@@ -494,7 +494,8 @@ __device__ inline void stage_top_nodes(const Job& J, uint4* top) {
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(128) k_shadow_pt(const Job J) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_shadow_pt(const Job J) {
   extern __shared__ uint4 top[];
   stage_top_nodes(J, top);
   const unsigned n = min(J.qctr[0], J.qcap);
@@ -628,8 +629,8 @@ __device__ inline bool walk_shade(const Job& J, WalkState& W, Trav& T) {
 }
 
 // phase: 0 = empty (wants a subpath), 1 = traversing, 2 = traversal finished (wants shading)
-template <int SHADE_THRESHOLD, int FETCH_THRESHOLD>
-__global__ void __launch_bounds__(128) k_walk_pt(const Job J) {
+template <int SHADE_THRESHOLD, int FETCH_THRESHOLD, int MINB = 4>
+__global__ void __launch_bounds__(128, MINB) k_walk_pt(const Job J) {
   extern __shared__ uint4 top[];
   stage_top_nodes(J, top);
   Trav T;
