@@ -231,7 +231,6 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
     if (ctx->variant == 1) k_walk_pt<16, 8, 4><<<g, threads, (size_t)J.ntop * 80, ctx->stream>>>(J);
     else k_walk_pt<16, 8, 6><<<g, threads, (size_t)J.ntop * 80, ctx->stream>>>(J);
   }
-  }
   else k_walk<<<(2 * J.B + threads - 1) / threads, threads, 0, ctx->stream>>>(J);
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 1), ctx->stream);
   const unsigned cgrid = (unsigned)((J.B + threads - 1) / threads) * (unsigned)(J.m + 1);
