@@ -436,6 +436,7 @@ int bdpt_upload_scene(BdptContext* ctx, const BdptCamera* camera, const BdptMate
   ctx->sc.nodes = ctx->d_nodes; ctx->sc.prims = ctx->d_prims; ctx->sc.shading = ctx->d_shading; ctx->sc.prims64 = ctx->d_prims64;
   ctx->sc.materials = ctx->d_mats; ctx->sc.lights = ctx->d_lights;
   ctx->sc.n_lights = (int)n_lights; ctx->sc.n_materials = (int)n_materials;
+  ctx->sc.qbias_bits = 0x47000000u;
   ctx->sc.n_nodes = (int)(bvh.nodes.size() / 20); ctx->sc.n_prims = (int)n_prims;
   ctx->bvh_nodes = (uint32_t)(bvh.nodes.size() / 20); ctx->bvh_depth = bvh.max_depth;
   ctx->sched = ctx->sched_req >= 0 ? ctx->sched_req : (ctx->bvh_nodes > 8 ? 1 : 0);

@@ -178,19 +178,25 @@ void build_bvh8(const std::vector<BuildPrim>& prims, Bvh8* out) {
       }
       cdone[bc] = true; slot_child[bs] = bc;
     }
-    // quantisation grid
-    float p[3]; uint32_t ebyte[3]; float scale[3];
+    // quantisation grid.  Every decoded plane keeps at least 1/64 of a quantum of slack to the box it
+    // bounds (the grid origin sits 1/32 quantum below the node's min corner): the traversal decodes a
+    // plane as fma(2^15 + q, a, b - 2^15 a), whose rounding error is below 1/512 quantum (traverse.cuh).
+    float p[3]; uint32_t ebyte[3]; float scale[3], slack[3];
     for (int a = 0; a < 3; a++) {
-      p[a] = top.box.lo[a];
-      float ext = top.box.hi[a] - top.box.lo[a];
+      const float lo = top.box.lo[a], hi = top.box.hi[a];
+      float ext = hi - lo;
       int e = -126;
       if (ext > 0.f) {
-        e = (int)std::ceil(std::log2((double)ext / 255.0));
+        e = (int)std::ceil(std::log2((double)ext / 254.9));
         e = std::max(-126, std::min(126, e));
-        while (e < 126 && std::ceil((double)ext / std::ldexp(1.0, e)) > 255.0) e++;
+      }
+      for (;; e++) {
+        scale[a] = std::ldexp(1.0f, e);
+        slack[a] = scale[a] * (1.0f / 64.0f);
+        p[a] = lo - 2.0f * slack[a];
+        if (e >= 126 || p[a] + 255.0f * scale[a] >= hi + slack[a]) break;
       }
       ebyte[a] = (uint32_t)(e + 127);
-      scale[a] = std::ldexp(1.0f, e);
     }
     uint8_t meta[8] = {0}, q[6][8];
     memset(q, 0, sizeof q);
@@ -207,9 +213,9 @@ void build_bvh8(const std::vector<BuildPrim>& prims, Bvh8* out) {
         double hi = ((double)cn.box.hi[a] - (double)p[a]) / (double)scale[a];
         int qlo = (int)std::floor(lo), qhi = (int)std::ceil(hi);
         qlo = std::max(0, std::min(255, qlo)); qhi = std::max(0, std::min(255, qhi));
-        // keep the decoded box conservative in fp32
-        while (qlo > 0 && p[a] + (float)qlo * scale[a] > cn.box.lo[a]) qlo--;
-        while (qhi < 255 && p[a] + (float)qhi * scale[a] < cn.box.hi[a]) qhi++;
+        // keep the decoded box conservative in fp32, with the slack the traversal's decode relies on
+        while (qlo > 0 && p[a] + (float)qlo * scale[a] > cn.box.lo[a] - slack[a]) qlo--;
+        while (qhi < 255 && p[a] + (float)qhi * scale[a] < cn.box.hi[a] + slack[a]) qhi++;
         q[a][s] = (uint8_t)qlo; q[3 + a][s] = (uint8_t)qhi;
       }
       if (cn.left >= 0) {

@@ -99,6 +99,9 @@ struct DScene {
   int n_materials;
   int n_nodes;
   int n_prims;
+  // 0x47000000 (the float 2^15).  Lives here so that the traversal's byte decode reads it from the kernel's
+  // constant bank: PRMT takes one immediate, and that slot goes to the byte selector (traverse.cuh, qbyte).
+  uint32_t qbias_bits;
 };
 
 __device__ inline float4 ldg4(const float4* p) { return __ldg(p); }

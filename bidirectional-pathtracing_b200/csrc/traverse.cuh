@@ -25,9 +25,13 @@ struct Hit {
   float b1, b2;
 };
 
-// byte k of w as a float without an int->float conversion: PRMT builds 0x4B0000bb (= 2^23 + bb)
-__device__ inline float ubyte(uint32_t w, int k) {
-  return __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7650u + (uint32_t)k)) - 8388608.0f;
+// byte k of w as the float 2^15 + bb, without an int->float conversion: PRMT builds 0x4700bb00.
+// The box test folds the 2^15 into its per-axis constant, so a quantised plane costs one PRMT and
+// one FFMA; the fold's rounding error (< 1/512 quantum) is inside the slack the builder leaves
+// (bvh8.cpp, "quantisation grid").
+#define BDPT_QBIAS 32768.0f
+__device__ inline float qbyte(uint32_t w, int k, uint32_t bias_bits) {   // bias_bits = DScene::qbias_bits
+  return __uint_as_float(__byte_perm(w, bias_bits, 0x7504u + ((uint32_t)k << 4)));
 }
 
 // Intersect one leaf primitive; returns true and shrinks tmax on an accepted hit.
@@ -109,13 +113,13 @@ struct Trav {
       q0 = ldg4(np); q1 = ldg4(np + 1); q2 = ldg4(np + 2); q3 = ldg4(np + 3); q4 = ldg4(np + 4);
     }
 
-    f3 adj, org;
+    f3 adj, org;   // plane q of an axis is hit at t = (2^15 + q) * adj + org
     adj.x = __uint_as_float((q0.w & 0xffu) << 23) * idir.x;
     adj.y = __uint_as_float(((q0.w >> 8) & 0xffu) << 23) * idir.y;
     adj.z = __uint_as_float(((q0.w >> 16) & 0xffu) << 23) * idir.z;
-    org.x = (__uint_as_float(q0.x) - o.x) * idir.x;
-    org.y = (__uint_as_float(q0.y) - o.y) * idir.y;
-    org.z = (__uint_as_float(q0.z) - o.z) * idir.z;
+    org.x = fmaf(-BDPT_QBIAS, adj.x, (__uint_as_float(q0.x) - o.x) * idir.x);
+    org.y = fmaf(-BDPT_QBIAS, adj.y, (__uint_as_float(q0.y) - o.y) * idir.y);
+    org.z = fmaf(-BDPT_QBIAS, adj.z, (__uint_as_float(q0.z) - o.z) * idir.z);
     const uint32_t imask = q0.w >> 24;
 
     // near / far plane words per axis, chosen by the direction sign
@@ -126,6 +130,16 @@ struct Trav {
     uint32_t nz0 = (oct & 4u) ? q4.z : q3.x, nz1 = (oct & 4u) ? q4.w : q3.y;
     uint32_t fz0 = (oct & 4u) ? q3.x : q4.z, fz1 = (oct & 4u) ? q3.y : q4.w;
 
+    // per child byte of the meta words, four children per 32-bit operation: the bit position a hit child
+    // sets (internal children: 24 + slot, mirrored by the ray octant so that the highest bit is the
+    // nearest child; leaves: their primitive offset) and the bits it sets there (1 / 11 / 111)
+    const uint32_t octinv4 = octinv * 0x01010101u;
+    const uint32_t in0 = (((q1.z & (q1.z << 1)) & 0x10101010u) >> 4) * 0xffu;
+    const uint32_t in1 = (((q1.w & (q1.w << 1)) & 0x10101010u) >> 4) * 0xffu;
+    const uint32_t pos0 = q1.z ^ (octinv4 & in0), pos1 = q1.w ^ (octinv4 & in1);
+    const uint32_t cnt0 = (q1.z >> 5) & 0x07070707u, cnt1 = (q1.w >> 5) & 0x07070707u;
+
+    const uint32_t qb = sc.qbias_bits;
     uint32_t hitmask = 0u;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -133,16 +147,15 @@ struct Trav {
       uint32_t nxw = i < 4 ? nx0 : nx1, fxw = i < 4 ? fx0 : fx1;
       uint32_t nyw = i < 4 ? ny0 : ny1, fyw = i < 4 ? fy0 : fy1;
       uint32_t nzw = i < 4 ? nz0 : nz1, fzw = i < 4 ? fz0 : fz1;
-      uint32_t meta = ((i < 4 ? q1.z : q1.w) >> (8 * k)) & 0xffu;
-      float t0 = fmaxf(fmaxf(ubyte(nxw, k) * adj.x + org.x, ubyte(nyw, k) * adj.y + org.y),
-                       fmaxf(ubyte(nzw, k) * adj.z + org.z, tmin));
-      float t1 = fminf(fminf(ubyte(fxw, k) * adj.x + org.x, ubyte(fyw, k) * adj.y + org.y),
-                       fminf(ubyte(fzw, k) * adj.z + org.z, hit.t));
+      float t0 = fmaxf(fmaxf(fmaf(qbyte(nxw, k, qb), adj.x, org.x), fmaf(qbyte(nyw, k, qb), adj.y, org.y)),
+                       fmaxf(fmaf(qbyte(nzw, k, qb), adj.z, org.z), tmin));
+      float t1 = fminf(fminf(fmaf(qbyte(fxw, k, qb), adj.x, org.x), fmaf(qbyte(fyw, k, qb), adj.y, org.y)),
+                       fminf(fmaf(qbyte(fzw, k, qb), adj.z, org.z), hit.t));
       t1 *= 1.0000004f;  // keep the cull conservative under fp32 rounding
-      if (t0 <= t1) {
-        uint32_t inner = (meta & 0x18u) == 0x18u ? octinv : 0u;
-        hitmask |= (meta >> 5) << ((meta ^ inner) & 31u);
-      }
+      const uint32_t pos = (i < 4 ? pos0 : pos1) >> (8 * k);             // the shift below uses its low 5 bits
+      const uint32_t cnt = ((i < 4 ? cnt0 : cnt1) >> (8 * k)) & 0xffu;
+      const uint32_t bits = cnt << (pos & 31u);
+      hitmask |= t0 <= t1 ? bits : 0u;
     }
     group = make_uint2(q1.x, (hitmask & 0xff000000u) | imask);
 

@@ -115,12 +115,17 @@ def main():
         return
     # converged reference renders (the reference's own binary, all host threads): the level-3 pin
     for name, (W, H, ns, m) in {"CBspheres_lambertian": (64, 48, 1024, 5), "CBspheres": (64, 48, 1024, 5),
-                                "CBgems": (64, 48, 1024, 5)}.items():
-        s, e, l, info = O.ref_render(O.ref_scene(name), W, H, ns, m, threads=os.cpu_count())
+                                "CBgems": (64, 48, 1024, 5), "CBbunny": (64, 48, 512, 5),
+                                "CBspheres_lambertian_occluded": (64, 48, 1024, 5), "CBgems_m16": (48, 36, 512, 16)}.items():
+        if only not in ("all", "converged") or (only == "converged" and os.path.exists(os.path.join(OUT, name + ".converged.npz"))):
+            continue
+        s, e, l, info = O.ref_render(O.ref_scene(name.split("_m")[0]), W, H, ns, m, threads=os.cpu_count())
         np.savez_compressed(os.path.join(OUT, name + ".converged.npz"), sum=s.astype(np.float32), eye=e.astype(np.float32),
                             light=l.astype(np.float32), params=np.array([W, H, ns, m]))
         print(name, "converged", info)
 
+    if only == "converged":
+        return
     # the author's PUBLISHED renders (assets/*_bdpt_128.png: 480x360, 128 spp, tone-mapped 8-bit) reduced to 60x45 box-filtered
     # means: a loose pin that is independent of our build of the reference (framing, tone map, overall light transport)
     from PIL import Image

@@ -205,13 +205,15 @@ def test_render_matches_oracle_same_random_numbers(api, O, name, m, roulette):
     assert close.mean() >= 0.95
 
 
-@pytest.mark.parametrize("name", ["CBspheres_lambertian", "CBspheres", "CBgems"])
+@pytest.mark.parametrize("name", ["CBspheres_lambertian", "CBspheres", "CBgems", "CBbunny", "CBspheres_lambertian_occluded",
+                                  "CBgems_m16"])       # "_m16": the same scene at max_ray_depth 16
 def test_converged_image_matches_reference_render(api, name):
     """Against the reference's OWN converged render (tests/golden/*.converged.npz, made by the
     reference binary with its own mt19937 streams): independent random numbers, so the bound is
     the reference's noise floor."""
     g = np.load(os.path.join(GOLDEN, name + ".converged.npz"))
     W, H, ns_ref, m = map(int, g["params"])
+    name = name.split("_m")[0]
     R = make_renderer(api, name, W, H, ns_aa=4096, max_ray_depth=m, seed=1)
     R.render()
     got = R.framebuffer(0)

@@ -150,12 +150,17 @@ def test_host_bvh_is_sound(name):
                     pid = int(order[slot])
                     assert not seen_prims[slot]; seen_prims[slot] = True
                     assert np.all(clo[s] <= lo[pid] + 1e-12) and np.all(chi[s] >= hi[pid] - 1e-12), "leaf box contains its primitive"
+                    # ... with the slack the traversal's folded byte decode relies on (bvh8.cpp "quantisation grid"),
+                    # up to what fp32 can represent at these coordinates
+                    ulp = np.spacing(np.maximum(np.abs(lo[pid]), np.abs(hi[pid])).astype(np.float32)).astype(np.float64)
+                    assert np.all(clo[s] <= lo[pid] - scale[i] / 128 + 4 * ulp) and np.all(chi[s] >= hi[pid] + scale[i] / 128 - 4 * ulp)
         if node_lo.get(i) is not None:
             plo, phi = node_lo[i]
             used = meta[i] != 0
-            # a node's own grid starts at its exact box and rounds outward by less than one of ITS quanta, so its
-            # children may stick out of the (also outward-rounded) slot box of the parent by at most that
-            assert np.all(clo[used].min(0) >= plo - 1e-6) and np.all(chi[used].max(0) <= phi + scale[i] + 1e-6), "child near parent's slot box"
+            # a node's own grid starts 1/32 of ITS quantum below its exact box and rounds outward by less than one
+            # quantum, so its children may stick out of the (also outward-rounded) slot box of the parent by that
+            assert (np.all(clo[used].min(0) >= plo - scale[i] / 16 - 1e-6)
+                    and np.all(chi[used].max(0) <= phi + scale[i] + 1e-6)), "child near parent's slot box"
     assert seen_nodes.all() and seen_prims.all()
 
 
