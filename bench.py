@@ -321,7 +321,8 @@ def main():
             "config": {"workload": desc, "scene": fixture, "prims": int(scene.n_prims), "width": W, "height": H, "spp": spp,
                        "max_ray_depth": m, "roulette": bool(roulette), "samples_per_step": samples_per_step,
                        "parallelism": f"sample-sharded x{world}, scene replicated, 1 NCCL reduce per accumulator",
-                       "l2_policy": "inputs larger than L2: each batch streams ~0.8 GB of vertex planes and up to 1.8 GB of shadow queue (L2 = 126 MB)"},
+                       "l2_policy": "inputs larger than L2: each batch of %d samples streams ~%.1f GB of vertex planes and ~%.1f GB of shadow queue (L2 = 126 MB)"
+                                    % (B, 64.0 * (verts + 1) * B / 1e9, 48.0 * shadow_per_sample * B / 1e9)},
             "mrays_per_s": value * rays_per_sample / 1e6, "rays_per_sample": rays_per_sample,
             "kernel_ms_first_batches": {**kern, "batches": tb, "batch_samples": B},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

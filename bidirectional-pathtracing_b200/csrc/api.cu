@@ -69,7 +69,10 @@ struct BdptContext {
   // of the tree (77 % L1 hit rate in k_walk_pt).
   int top_nodes = 0;
   int connect_minb = 6; // __launch_bounds__ min blocks of k_connect (BDPT_CONNECT_MINB, tuning only)
-  int batch_log2 = 22, batch_gib = 12;  // batch size cap (samples) and its memory budget (BDPT_BATCH_LOG2, BDPT_BATCH_GIB)
+  // batch size cap (samples) and its memory budget (BDPT_BATCH_LOG2, BDPT_BATCH_GIB).  The persistent kernels end
+  // with a tail of long paths; at 2^24 samples per batch that tail is ~1 % of the step (2^22: ~4 %), and 48 of the
+  // 180 GB are there to be used.  Storage is only ever allocated for the samples a render actually has.
+  int batch_log2 = 24, batch_gib = 48;
   int walk_ctas = 6, shadow_ctas = 8;  // resident CTAs per SM of the persistent kernels
 };
 

@@ -27,7 +27,7 @@ def run(env):
     return img
 
 base = run({})
-variants = [{"BDPT_SCHED": 0}, {"BDPT_VARIANT": 1, "BDPT_WALK_CTAS": 4}, {"BDPT_SHADOW_CTAS": 6}]
+variants = [{"BDPT_SCHED": 0}, {"BDPT_VARIANT": 1, "BDPT_WALK_CTAS": 4}, {"BDPT_BATCH_LOG2": 22, "BDPT_BATCH_GIB": 12}]
 for v in variants:
     img = run(v)
     d = np.abs(img - base)
