@@ -69,11 +69,13 @@ struct BdptContext {
   // of the tree (77 % L1 hit rate in k_walk_pt).
   int top_nodes = 0;
   int connect_minb = 6; // __launch_bounds__ min blocks of k_connect (BDPT_CONNECT_MINB, tuning only)
+  int traits = 0;       // BDPT_TRAIT_* of the uploaded scene
+  int spec = 7;         // which kernels may use their trait-specialised build: 1 walk, 2 connect, 4 shadow (BDPT_SPEC, tuning only)
   // batch size cap (samples) and its memory budget (BDPT_BATCH_LOG2, BDPT_BATCH_GIB).  The persistent kernels end
   // with a tail of long paths; at 2^24 samples per batch that tail is ~1 % of the step (2^22: ~4 %), and 48 of the
   // 180 GB are there to be used.  Storage is only ever allocated for the samples a render actually has.
   int batch_log2 = 24, batch_gib = 48;
-  int walk_ctas = 6, shadow_ctas = 8;  // resident CTAs per SM of the persistent kernels
+  int walk_ctas = 6, shadow_ctas = 0;  // resident CTAs per SM of the persistent kernels (shadow: 0 = the build's own, 10 or 8)
 };
 
 namespace {
@@ -222,7 +224,7 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
     k_wf_gen<<<(n2 + threads - 1) / threads, threads, 0, ctx->stream>>>(J, F);
     for (int b = 0; b < J.m; b++) {
       F.ctr = ctr0 + 4 * b;
-      k_wf_trace<<<ctx->sm_count * ctx->shadow_ctas, threads, 0, ctx->stream>>>(J, F, b == 0 ? n2 : 0u);
+      k_wf_trace<<<ctx->sm_count * (ctx->shadow_ctas > 0 ? ctx->shadow_ctas : 8), threads, 0, ctx->stream>>>(J, F, b == 0 ? n2 : 0u);
       k_wf_shade<<<(n2 + threads - 1) / threads, threads, 0, ctx->stream>>>(J, F, b == 0 ? n2 : 0u);
       std::swap(F.queue_a, F.queue_b);   // this bounce's survivors are the next bounce's input
     }
@@ -231,20 +233,48 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
     const int g = ctx->sm_count * ctx->walk_ctas;
     // 6 CTAs/SM (80 registers, ~0.2 KB of spills) beats 4 CTAs at 101 registers by 6 %: the state machine is
     // latency-bound between votes.  BDPT_VARIANT=1 selects the unspilled build for comparison.
-    if (ctx->variant == 1) k_walk_pt<16, 8, 4><<<g, threads, (size_t)J.ntop * 80, ctx->stream>>>(J);
-    else k_walk_pt<16, 8, 6><<<g, threads, (size_t)J.ntop * 80, ctx->stream>>>(J);
+    const size_t shm = (size_t)J.ntop * 80;
+    if (ctx->variant == 1) k_walk_pt<16, 8, 4><<<g, threads, shm, ctx->stream>>>(J);
+    else switch ((ctx->spec & 1) ? ctx->traits : 0) {
+      case 1: k_walk_pt<16, 8, 6, 1><<<g, threads, shm, ctx->stream>>>(J); break;
+      case 2: k_walk_pt<16, 8, 6, 2><<<g, threads, shm, ctx->stream>>>(J); break;
+      case 3: k_walk_pt<16, 8, 6, 3><<<g, threads, shm, ctx->stream>>>(J); break;
+      default: k_walk_pt<16, 8, 6, 0><<<g, threads, shm, ctx->stream>>>(J); break;
+    }
   }
   else k_walk<<<(2 * J.B + threads - 1) / threads, threads, 0, ctx->stream>>>(J);
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 1), ctx->stream);
   const unsigned cgrid = (unsigned)((J.B + threads - 1) / threads) * (unsigned)(J.m + 1);
-  switch (TRACE ? 0 : ctx->connect_minb) {
-    case 4: k_connect<TRACE, 4><<<cgrid, threads, 0, ctx->stream>>>(J); break;
-    case 6: k_connect<TRACE, 6><<<cgrid, threads, 0, ctx->stream>>>(J); break;
-    case 8: k_connect<TRACE, 8><<<cgrid, threads, 0, ctx->stream>>>(J); break;
+  const bool lambert = !TRACE && (ctx->spec & 2) && (ctx->traits & BDPT_TRAIT_LAMBERT);
+  // The Lambert build needs 96 registers unspilled and runs best that way (5 CTAs/SM); forced to 80 registers it is
+  // slower than the generic build at 80, which tolerates its spills (measured: 6.3 / 9.7 / 7.2 ms per 2^24 samples).
+  switch (TRACE ? 0 : (lambert && ctx->connect_minb == 6 ? 4 : ctx->connect_minb)) {
+    case 4:
+      if (lambert) k_connect<TRACE, 4, BDPT_TRAIT_LAMBERT><<<cgrid, threads, 0, ctx->stream>>>(J);
+      else k_connect<TRACE, 4><<<cgrid, threads, 0, ctx->stream>>>(J);
+      break;
+    case 6:
+      if (lambert) k_connect<TRACE, 6, BDPT_TRAIT_LAMBERT><<<cgrid, threads, 0, ctx->stream>>>(J);
+      else k_connect<TRACE, 6><<<cgrid, threads, 0, ctx->stream>>>(J);
+      break;
+    case 8:
+      if (lambert) k_connect<TRACE, 8, BDPT_TRAIT_LAMBERT><<<cgrid, threads, 0, ctx->stream>>>(J);
+      else k_connect<TRACE, 8><<<cgrid, threads, 0, ctx->stream>>>(J);
+      break;
     default: k_connect<TRACE, 3><<<cgrid, threads, 0, ctx->stream>>>(J); break;
   }
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 2), ctx->stream);
-  if (ctx->sched) k_shadow_pt<8><<<ctx->sm_count * ctx->shadow_ctas, threads, (size_t)J.ntop * 80, ctx->stream>>>(J);
+  if (ctx->sched) {
+    // triangles only: 48 registers (28 B of spills) and 10 CTAs/SM; with the sphere test compiled in, 64 and 8
+    const size_t shm = (size_t)J.ntop * 80;
+    if ((ctx->spec & 4) && (ctx->traits & BDPT_TRAIT_TRIS)) {
+      const int c = ctx->shadow_ctas > 0 ? ctx->shadow_ctas : 10;
+      k_shadow_pt<10, BDPT_TRAIT_TRIS><<<ctx->sm_count * c, threads, shm, ctx->stream>>>(J);
+    } else {
+      const int c = ctx->shadow_ctas > 0 ? ctx->shadow_ctas : 8;
+      k_shadow_pt<8><<<ctx->sm_count * c, threads, shm, ctx->stream>>>(J);
+    }
+  }
   else k_shadow<<<ctx->sm_count * 8, threads, 0, ctx->stream>>>(J);
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 3), ctx->stream);
   ctx->stats.kernel_launches += 3;
@@ -308,6 +338,7 @@ int bdpt_create(int device, BdptContext** out) {
   if (const char* e = getenv("BDPT_BATCH_GIB")) ctx->batch_gib = std::min(64, std::max(1, atoi(e)));
   if (const char* e = getenv("BDPT_TOP_NODES")) ctx->top_nodes = std::max(0, std::min(512, atoi(e)));
   if (const char* e = getenv("BDPT_CONNECT_MINB")) ctx->connect_minb = atoi(e);
+  if (const char* e = getenv("BDPT_SPEC")) ctx->spec = atoi(e);
   if (const char* e = getenv("BDPT_VARIANT")) ctx->variant = atoi(e);
   if (const char* e = getenv("BDPT_WALK_CTAS")) ctx->walk_ctas = std::max(1, atoi(e));
   if (const char* e = getenv("BDPT_SHADOW_CTAS")) ctx->shadow_ctas = std::max(1, atoi(e));
@@ -443,6 +474,12 @@ int bdpt_upload_scene(BdptContext* ctx, const BdptCamera* camera, const BdptMate
   ctx->sc.n_nodes = (int)(bvh.nodes.size() / 20); ctx->sc.n_prims = (int)n_prims;
   ctx->bvh_nodes = (uint32_t)(bvh.nodes.size() / 20); ctx->bvh_depth = bvh.max_depth;
   ctx->sched = ctx->sched_req >= 0 ? ctx->sched_req : (ctx->bvh_nodes > 8 ? 1 : 0);
+  // what this scene promises the specialised kernels (common.cuh, BDPT_TRAIT_*)
+  int traits = BDPT_TRAIT_TRIS | BDPT_TRAIT_LAMBERT;
+  for (uint32_t i = 0; i < n_prims; i++) if (prims[i].type != BDPT_PRIM_TRIANGLE) { traits &= ~BDPT_TRAIT_TRIS; break; }
+  for (uint32_t i = 0; i < n_materials; i++)
+    if (materials[i].type != BDPT_MAT_DIFFUSE && materials[i].type != BDPT_MAT_EMISSION) { traits &= ~BDPT_TRAIT_LAMBERT; break; }
+  ctx->traits = traits;
   ctx->cam_base = *camera;
   ctx->have_scene = true;
   if (ctx->W > 0) make_dcamera(ctx->cam_base, ctx->W, ctx->H, &ctx->cam);

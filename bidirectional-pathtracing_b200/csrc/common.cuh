@@ -88,6 +88,13 @@ struct alignas(16) Node8 {  // 80 bytes, see bvh8.h
   uint4 q[5];
 };
 
+// Scene traits the hot kernels are specialised on (decided once per scene at upload, api.cu).  The walk kernel is
+// bound by instruction fetch (71 KB of SASS when every material and both primitive kinds are compiled in); most
+// scenes of the reference are triangle meshes with Lambertian surfaces, and the kernels built for those traits are
+// half the size.  A trait is a promise about the scene's contents, never a change of behaviour.
+#define BDPT_TRAIT_TRIS 1      // every primitive is a triangle
+#define BDPT_TRAIT_LAMBERT 2   // every material is DiffuseBSDF or EmissionBSDF
+
 struct DScene {
   const uint4* nodes;       // Node8 as 5 x uint4
   const float4* prims;      // leaf-ordered primitive records, 3 x float4 each

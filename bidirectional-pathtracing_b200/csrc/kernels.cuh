@@ -232,7 +232,7 @@ struct GlobalVerts {
   __device__ inline void light_origin(float4* a, float4* b) const { size_t s1 = VSLOT(J, 1, 1, si); *a = J.v0[s1]; *b = J.v1[s1]; }
 };
 // All strategies (s = 0 .. nL) of one (sample, t): estimate_bidirection_radiance + the closed-form MIS weight.
-template <bool TRACE, class VERTS>
+template <bool TRACE, int TR, class VERTS>
 __device__ inline void connect_strategies(const Job& J, const int si, const int t, const int nL, const VERTS& V) {
   int x, y, sample;
   decode_sample(J, J.g0 + (unsigned long long)si, &x, &y, &sample);
@@ -243,7 +243,7 @@ __device__ inline void connect_strategies(const Job& J, const int si, const int 
   E.mat = -1; E.D = 1.f; E.S = 0.f; E.q = 1.f;
   if (t >= 2) {
     E = V.get(0, t);
-    ME = load_mat(sc, E.mat);
+    ME = load_mat<TR>(sc, E.mat);
   } else {
     E.pos = J.cam.pos; E.alpha = mk3(1.f); E.n = zero; E.wo = zero;
     ME.type = -1;
@@ -279,7 +279,7 @@ __device__ inline void connect_strategies(const Job& J, const int si, const int 
         bool delta_prev = false;
         if (t >= 3) {
           Vtx P = V.get(0, t - 1);
-          delta_prev = type_is_delta(mat_type(sc, P.mat));
+          delta_prev = type_is_delta(mat_type<TR>(sc, P.mat));
           if (P.S > 0.f) {
             float pp, dp;
             light_sample_pdf(L, E.pos, -E.wo, &pp, &dp);  // dir pdf of leaving the light toward e_{t-1}
@@ -315,7 +315,7 @@ __device__ inline void connect_strategies(const Job& J, const int si, const int 
         ML.type = -1;
       } else {
         Lv = V.get(1, s);
-        ML = load_mat(sc, Lv.mat);
+        ML = load_mat<TR>(sc, Lv.mat);
       }
       // ---- eye-side endpoint ve (t == 1: the pinhole, bidirection.cpp:360-383)
       f3 ve_pos = E.pos, ve_n = E.n, eye_alpha = E.alpha;
@@ -357,7 +357,7 @@ __device__ inline void connect_strategies(const Job& J, const int si, const int 
             f3 wv = P.pos - E.pos; float d2 = dot(wv, wv);
             float gp = fabsf(woEz * dot(wv * rsqrtf(d2), P.n)) / d2;
             float R = bsdf_pdf_mis_z(ME, cEz, woEz, dotE) * E.q * gp / P.D;
-            S_t = clampS((type_is_delta(mat_type(sc, P.mat)) ? 0.f : 1.f) + (P.S > 0.f ? R * R * P.S : 0.f));
+            S_t = clampS((type_is_delta(mat_type<TR>(sc, P.mat)) ? 0.f : 1.f) + (P.S > 0.f ? R * R * P.S : 0.f));
           }
           winv += (double)r_t * (double)r_t * (double)S_t;
         }
@@ -370,7 +370,7 @@ __device__ inline void connect_strategies(const Job& J, const int si, const int 
             f3 wv = P.pos - Lv.pos; float d2 = dot(wv, wv);
             float gp = fabsf(woLz * dot(wv * rsqrtf(d2), P.n)) / d2;
             float R = bsdf_pdf_mis_z(ML, cLz, woLz, dotL) * Lv.q * gp / P.D;
-            bool dprev = s - 1 >= 2 && type_is_delta(mat_type(sc, P.mat));
+            bool dprev = s - 1 >= 2 && type_is_delta(mat_type<TR>(sc, P.mat));
             S_s = clampS((dprev ? 0.f : 1.f) + (P.S > 0.f ? R * R * P.S : 0.f));
           }
           winv += (double)r_s * (double)r_s * (double)S_s;
@@ -399,7 +399,7 @@ __device__ inline void connect_strategies(const Job& J, const int si, const int 
       }
       if (TRACE) {
         // trace mode resolves visibility inline so that the record says "occluded" (NaN) like the oracle's
-        Hit h = traverse<true>(sc, ve_pos, cdir, BDPT_EPS_F, dist - BDPT_EPS_F);
+        Hit h = traverse<true, TR>(sc, ve_pos, cdir, BDPT_EPS_F, dist - BDPT_EPS_F);
         if (h.leaf >= 0) { contrib = mk3(NAN); w = NAN; push = false; eye_x = eye_y = -1; }
       }
       push_shadow(J, push, ve_pos, cdir, dist - BDPT_EPS_F, target, ill);
@@ -415,7 +415,7 @@ __device__ inline void connect_strategies(const Job& J, const int si, const int 
 
 // One thread per (sample, t), vertices read from HBM/L2 as needed.  Grid: 1-D, the (m+1) values of t of
 // one group of 128 samples are consecutive blocks, so the light vertices they share meet in L2.
-template <bool TRACE, int MINB>
+template <bool TRACE, int MINB, int TR = 0>
 __global__ void __launch_bounds__(128, MINB) k_connect(const Job J) {
   const int t = (int)(blockIdx.x % (unsigned)(J.m + 1)) + 1;
   const int si = (int)(blockIdx.x / (unsigned)(J.m + 1)) * blockDim.x + threadIdx.x;
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(128, MINB) k_connect(const Job J) {
   const int nL = J.counts[J.B + si];
   if (nE == 0 || t > nE) return;  // invalid lane or the eye subpath is shorter than t
   GlobalVerts V{J, si};
-  connect_strategies<TRACE>(J, si, t, nL, V);
+  connect_strategies<TRACE, TR>(J, si, t, nL, V);
 }
 
 // -------------------------------------------------------------------------------------- shadow
@@ -494,7 +494,7 @@ __device__ inline void stage_top_nodes(const Job& J, uint4* top) {
   __syncthreads();
 }
 
-template <int MINB>
+template <int MINB, int TR = 0>
 __global__ void __launch_bounds__(128, MINB) k_shadow_pt(const Job J) {
   extern __shared__ uint4 top[];
   stage_top_nodes(J, top);
@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(128, MINB) k_shadow_pt(const Job J) {
       if (wf.exhausted) break;
       continue;
     }
-    if (active && T.step<true>(J.sc, stack, top, (uint32_t)J.ntop)) {
+    if (active && T.step<true, TR>(J.sc, stack, top, (uint32_t)J.ntop)) {
       traced++;
       active = false;
       if (T.hit.leaf < 0) {
@@ -581,16 +581,17 @@ __device__ inline bool walk_begin(const Job& J, unsigned i, WalkState& W, Trav& 
 // The traversal of the current ray finished: store the vertex (if any) and sample the next ray
 // (body of the while loop of prepare_bidirectional_subpath, bidirection.cpp:44-101).
 // Returns true if the subpath continues (T holds the next ray), false if it ended.
+template <int TR = 0>
 __device__ inline bool walk_shade(const Job& J, WalkState& W, Trav& T) {
   const DScene& sc = J.sc;
   if (T.hit.leaf < 0) return false;
   const f3 o = T.o, d = T.d;
   f3 n, hit_p; int prim, mat;
-  finish_hit(sc, T.hit, o, d, &n, &prim, &mat, &hit_p);
+  finish_hit<TR>(sc, T.hit, o, d, &n, &prim, &mat, &hit_p);
   const float t = T.hit.t;
   const Frame fr = make_frame(n);
   const f3 w_out = fr.to_local(-d);
-  const Mat M = load_mat(sc, mat);
+  const Mat M = load_mat<TR>(sc, mat);
   f3 wi; float pdf;
   const f3 f = bsdf_sample_f(M, w_out, &wi, &pdf, W.rng);
   const f3 wi_world = normalized(fr.to_world(wi));
@@ -629,7 +630,7 @@ __device__ inline bool walk_shade(const Job& J, WalkState& W, Trav& T) {
 }
 
 // phase: 0 = empty (wants a subpath), 1 = traversing, 2 = traversal finished (wants shading)
-template <int SHADE_THRESHOLD, int FETCH_THRESHOLD, int MINB = 4>
+template <int SHADE_THRESHOLD, int FETCH_THRESHOLD, int MINB = 4, int TR = 0>
 __global__ void __launch_bounds__(128, MINB) k_walk_pt(const Job J) {
   extern __shared__ uint4 top[];
   stage_top_nodes(J, top);
@@ -647,7 +648,7 @@ __global__ void __launch_bounds__(128, MINB) k_walk_pt(const Job J) {
     // shading waits until enough lanes want it (or nothing else can run) ...
     if (shade != 0u && (trav == 0u || __popc(shade) >= SHADE_THRESHOLD)) {
       if (phase == 2) {
-        if (walk_shade(J, W, T)) phase = 1;
+        if (walk_shade<TR>(J, W, T)) phase = 1;
         else { J.counts[W.kind * J.B + W.si] = W.nv; phase = 0; }
       }
     }
@@ -659,7 +660,7 @@ __global__ void __launch_bounds__(128, MINB) k_walk_pt(const Job J) {
     }
     if (__ballot_sync(0xffffffffu, phase != 0) == 0u && wf.exhausted) break;
     if (phase == 1) {
-      if (T.step<false>(J.sc, stack, top, (uint32_t)J.ntop)) { phase = 2; nrays++; }
+      if (T.step<false, TR>(J.sc, stack, top, (uint32_t)J.ntop)) { phase = 2; nrays++; }
     }
   }
   unsigned int tot = __reduce_add_sync(0xffffffffu, nrays);

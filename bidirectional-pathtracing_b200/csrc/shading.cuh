@@ -15,17 +15,26 @@ struct Mat {
   float alpha, ior;
 };
 
-__device__ inline int mat_type(const DScene& sc, int m) { return __float_as_int(ldg4(sc.materials + 5 * m).w); }
+template <int TR = 0>
+__device__ inline int mat_type(const DScene& sc, int m) {
+  if (TR & BDPT_TRAIT_LAMBERT) return BDPT_MAT_DIFFUSE;   // callers only ask whether the type is a delta type
+  return __float_as_int(ldg4(sc.materials + 5 * m).w);
+}
 
 __device__ inline bool type_is_delta(int type) {  // BSDF::is_delta of each class, bsdf.h
   return type == BDPT_MAT_MIRROR || type == BDPT_MAT_GLASS || type == BDPT_MAT_REFRACTION;
 }
 
+template <int TR = 0>
 __device__ inline Mat load_mat(const DScene& sc, int m) {
   Mat r;
   const float4* p = sc.materials + 5 * m;
   float4 a = ldg4(p), b = ldg4(p + 1), c = ldg4(p + 2);
   r.reflectance = mk3(a.x, a.y, a.z); r.type = __float_as_int(a.w);
+  if (TR & BDPT_TRAIT_LAMBERT) {   // lets the compiler drop every other BSDF from the caller
+    if (r.type != BDPT_MAT_EMISSION) r.type = BDPT_MAT_DIFFUSE;
+    __builtin_assume(r.type == BDPT_MAT_DIFFUSE || r.type == BDPT_MAT_EMISSION);
+  }
   r.transmittance = mk3(b.x, b.y, b.z); r.ior = b.w;
   r.radiance = mk3(c.x, c.y, c.z); r.alpha = c.w;
   if (r.type == BDPT_MAT_MICROFACET) {

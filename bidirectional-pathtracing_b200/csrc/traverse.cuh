@@ -35,10 +35,11 @@ __device__ inline float qbyte(uint32_t w, int k, uint32_t bias_bits) {   // bias
 }
 
 // Intersect one leaf primitive; returns true and shrinks tmax on an accepted hit.
+template <int TR = 0>
 __device__ inline bool intersect_prim(const float4* __restrict__ prims, int k, f3 o, f3 d, float tmin, float& tmax,
                                       float& b1o, float& b2o) {
   float4 a = ldg4(prims + 3 * k), b = ldg4(prims + 3 * k + 1);
-  if (__float_as_int(b.w) >= 0) {  // triangle: a = {v0, prim id}, b = {e1, material}, c = {e2, -}
+  if ((TR & BDPT_TRAIT_TRIS) || __float_as_int(b.w) >= 0) {  // triangle: a = {v0, prim id}, b = {e1, material}, c = {e2, -}
     float4 c = ldg4(prims + 3 * k + 2);
     f3 e1 = mk3(b.x, b.y, b.z), e2 = mk3(c.x, c.y, c.z);
     f3 s = o - mk3(a.x, a.y, a.z);
@@ -92,7 +93,7 @@ struct Trav {
   // scalar state stays in registers)
   // `top` (optional): the first `ntop` nodes of the tree — its upper levels, the builder emits nodes breadth
   // first — staged in shared memory by the calling kernel.
-  template <bool ANY_HIT>
+  template <bool ANY_HIT, int TR = 0>
   __device__ inline bool step(const DScene& sc, uint2* stack, const uint4* top = nullptr, const uint32_t ntop = 0) {
     const uint32_t octinv = oct ^ 7u;
     // ---- pop the nearest internal child of the current group
@@ -165,7 +166,7 @@ struct Trav {
       int i = __ffs(tris) - 1;
       tris &= tris - 1u;
       int k = (int)q1.y + i;
-      if (intersect_prim(sc.prims, k, o, d, tmin, hit.t, hit.b1, hit.b2)) {
+      if (intersect_prim<TR>(sc.prims, k, o, d, tmin, hit.t, hit.b1, hit.b2)) {
         hit.leaf = k;
         if (ANY_HIT) return true;
       }
@@ -178,12 +179,12 @@ struct Trav {
   }
 };
 
-template <bool ANY_HIT>
+template <bool ANY_HIT, int TR = 0>
 __device__ inline Hit traverse(const DScene& sc, f3 o, f3 d, float tmin, float tmax) {
   Trav T;
   uint2 stack[BDPT_STACK];
   T.begin(o, d, tmin, tmax);
-  while (!T.template step<ANY_HIT>(sc, stack)) {}
+  while (!T.template step<ANY_HIT, TR>(sc, stack)) {}
   return T.hit;
 }
 
@@ -195,6 +196,7 @@ __device__ inline Hit traverse(const DScene& sc, f3 o, f3 d, float tmin, float t
 // t and the barycentrics then agree with the fp64 reference to ~1e-12 relative instead of the
 // ~1e-4 an fp32 Moller-Trumbore gives at grazing incidence, which keeps hit points on their
 // surface and the EPS_F = 1e-5 self-intersection offsets meaningful.
+template <int TR = 0>
 __device__ inline void finish_hit(const DScene& sc, Hit& h, f3 o, f3 d, f3* n, int* prim_id, int* mat, f3* hit_p) {
   float4 a = ldg4(sc.prims + 3 * h.leaf), b = ldg4(sc.prims + 3 * h.leaf + 1);
   *prim_id = __float_as_int(a.w);
@@ -202,7 +204,7 @@ __device__ inline void finish_hit(const DScene& sc, Hit& h, f3 o, f3 d, f3* n, i
   *mat = mw & 0x7fffffff;
   const double* g = sc.prims64 + 10 * (size_t)h.leaf;
   const double ox = o.x, oy = o.y, oz = o.z, dx = d.x, dy = d.y, dz = d.z;
-  if (mw >= 0) {
+  if ((TR & BDPT_TRAIT_TRIS) || mw >= 0) {
     const double2 g0 = __ldg((const double2*)g), g1 = __ldg((const double2*)g + 1), g2 = __ldg((const double2*)g + 2),
                   g3 = __ldg((const double2*)g + 3), g4 = __ldg((const double2*)g + 4);
     const double p1x = g0.x, p1y = g0.y, p1z = g1.x;

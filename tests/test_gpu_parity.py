@@ -205,6 +205,32 @@ def test_render_matches_oracle_same_random_numbers(api, O, name, m, roulette):
     assert close.mean() >= 0.95
 
 
+# Every build of the hot kernels.  The library picks kernels by scene: the one-subpath-per-lane forms for BVHs of <= 8
+# nodes, else the persistent forms, compiled per scene trait (triangles only / Lambertian only, csrc/common.cuh).  The
+# fixtures above therefore never run e.g. the persistent kernels with spheres and glass; the tuning knobs force them.
+@pytest.mark.parametrize("name,env", [
+    ("CBspheres", {"BDPT_SCHED": "1"}),                    # persistent kernels, no trait (spheres, mirror + glass)
+    ("CBspheres_microfacet_al_ag", {"BDPT_SCHED": "1"}),   # ... with microfacet MIS
+    ("CBspheres_lambertian", {"BDPT_SCHED": "1"}),         # persistent, Lambertian trait only
+    ("CBbunny", {"BDPT_SPEC": "0"}),                       # triangle + Lambertian scene on the untraited build
+    ("CBgems", {"BDPT_SPEC": "0"}),                        # triangle scene with delta materials on the untraited build
+    ("CBbunny", {"BDPT_SCHED": "0"}),                      # one subpath per lane on a deep BVH
+    ("CBgems", {"BDPT_SCHED": "2"}),                       # per-bounce wavefront walk
+])
+def test_every_kernel_build_matches_oracle(api, O, name, env, monkeypatch):
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)      # read once, at bdpt_create
+    W, H, ns, m = 48, 36, 8, 5
+    R = make_renderer(api, name, W, H, ns_aa=ns, max_ray_depth=m, seed=23)
+    R.render()
+    gs, ge, gl = (R.framebuffer(i).astype(np.float64) for i in range(3))
+    R.close()
+    os_, oe, ol, _ = O.Oracle(load_scene(name), W, H).render(ns, m, rng_mode=1, seed=23, threads=8)
+    assert np.isfinite(gs).all()
+    assert abs(gs.mean() - os_.mean()) <= 1e-3 * os_.mean()
+    assert relmse(gs, os_) <= 1e-3 and relmse(ge, oe) <= 1e-3 and relmse(gl, ol) <= 1e-3
+
+
 @pytest.mark.parametrize("name", ["CBspheres_lambertian", "CBspheres", "CBgems", "CBbunny", "CBspheres_lambertian_occluded",
                                   "CBgems_m16"])       # "_m16": the same scene at max_ray_depth 16
 def test_converged_image_matches_reference_render(api, name):
