@@ -44,7 +44,7 @@ __device__ inline bool intersect_prim(const float4* __restrict__ prims, int k, f
     f3 e1 = mk3(b.x, b.y, b.z), e2 = mk3(c.x, c.y, c.z);
     f3 s = o - mk3(a.x, a.y, a.z);
     f3 s1 = cross(d, e2), s2 = cross(s, e1);
-    float inv = 1.0f / dot(s1, e1);
+    float inv = __fdividef(1.0f, dot(s1, e1));   // MUFU.RCP, <= 2 ulp: the winner is re-intersected in fp64 (finish_hit)
     float t = dot(s2, e2) * inv, b1 = dot(s1, s) * inv, b2 = dot(s2, d) * inv;
     if (t >= tmin && t <= tmax && b1 >= 0.f && b2 >= 0.f && b1 + b2 <= 1.f) {
       tmax = t; b1o = b1; b2o = b2;
