@@ -494,6 +494,14 @@ __device__ inline void stage_top_nodes(const Job& J, uint4* top) {
   __syncthreads();
 }
 
+// Adds an unoccluded connection to its pixel (queue entry idx).
+__device__ inline void shadow_splat(const Job& J, unsigned idx) {
+  float4 b = J.q1[idx], c = J.q2[idx];
+  unsigned int tg = __float_as_uint(b.w);
+  float* px = ((tg & 0x80000000u) ? J.acc_light : J.acc_eye) + 3 * (size_t)(tg & 0x7fffffffu);
+  atomicAdd(px + 0, c.x); atomicAdd(px + 1, c.y); atomicAdd(px + 2, c.z);
+}
+
 template <int MINB, int TR = 0>
 __global__ void __launch_bounds__(128, MINB) k_shadow_pt(const Job J) {
   extern __shared__ uint4 top[];
@@ -503,10 +511,16 @@ __global__ void __launch_bounds__(128, MINB) k_shadow_pt(const Job J) {
   uint2 stack[BDPT_STACK];
   bool active = false;
   unsigned idx = 0, traced = 0;
+  // Rays end a few lanes at a time (ncu: the splat ran at 4-6 lanes).  A lane parks its unoccluded ray here and goes
+  // on with the next one; the warp splats when half of its lanes have one parked.
+  unsigned pend = BDPT_NONE;
   WarpFetch wf; wf.next = 0; wf.end = 0; wf.exhausted = false;
 #pragma unroll 1
   for (;;) {
     const unsigned idle = __ballot_sync(0xffffffffu, !active);
+    if (__popc(__ballot_sync(0xffffffffu, pend != BDPT_NONE)) >= 16) {
+      if (pend != BDPT_NONE) { shadow_splat(J, pend); pend = BDPT_NONE; }
+    }
     if (!wf.exhausted && (__popc(idle) >= 4 || idle == 0xffffffffu)) {
       unsigned my = warp_fetch(J.qctr + 1, n, 256u, !active, wf);
       if (my != BDPT_NONE) {
@@ -523,13 +537,12 @@ __global__ void __launch_bounds__(128, MINB) k_shadow_pt(const Job J) {
       traced++;
       active = false;
       if (T.hit.leaf < 0) {
-        float4 b = J.q1[idx], c = J.q2[idx];
-        unsigned int tg = __float_as_uint(b.w);
-        float* px = ((tg & 0x80000000u) ? J.acc_light : J.acc_eye) + 3 * (size_t)(tg & 0x7fffffffu);
-        atomicAdd(px + 0, c.x); atomicAdd(px + 1, c.y); atomicAdd(px + 2, c.z);
+        if (pend != BDPT_NONE) shadow_splat(J, pend);   // the slot is taken: this lane cannot wait for the warp
+        pend = idx;
       }
     }
   }
+  if (pend != BDPT_NONE) shadow_splat(J, pend);
   unsigned int tot = __reduce_add_sync(0xffffffffu, traced);
   if ((threadIdx.x & 31) == 0 && tot) atomicAdd(J.stats + 1, (unsigned long long)tot);
 }

@@ -82,9 +82,10 @@ struct Trav {
     o = o_; d = d_; tmin = tmin_;
     hit.t = tmax_; hit.leaf = -1; hit.b1 = 0.f; hit.b2 = 0.f;
     oct = (d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u);
-    idir.x = 1.0f / (fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x));
-    idir.y = 1.0f / (fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y));
-    idir.z = 1.0f / (fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z));
+    // MUFU.RCP (<= 2 ulp): the reciprocals only feed the box cull, whose slack factor below covers them
+    idir.x = __fdividef(1.0f, fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x));
+    idir.y = __fdividef(1.0f, fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y));
+    idir.z = __fdividef(1.0f, fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z));
     sp = 0;
     group = make_uint2(0u, 0x80000000u);  // root: node 0, top priority bit
   }
@@ -152,7 +153,7 @@ struct Trav {
                        fmaxf(fmaf(qbyte(nzw, k, qb), adj.z, org.z), tmin));
       float t1 = fminf(fminf(fmaf(qbyte(fxw, k, qb), adj.x, org.x), fmaf(qbyte(fyw, k, qb), adj.y, org.y)),
                        fminf(fmaf(qbyte(fzw, k, qb), adj.z, org.z), hit.t));
-      t1 *= 1.0000004f;  // keep the cull conservative under fp32 rounding
+      t1 *= 1.000001f;  // keep the cull conservative under fp32 rounding (8 ulp: two 2-ulp reciprocals + the FMAs)
       const uint32_t pos = (i < 4 ? pos0 : pos1) >> (8 * k);             // the shift below uses its low 5 bits
       const uint32_t cnt = ((i < 4 ? cnt0 : cnt1) >> (8 * k)) & 0xffu;
       const uint32_t bits = cnt << (pos & 31u);
