@@ -72,6 +72,7 @@ struct BdptContext {
   int top_nodes = 0;
   int connect_minb = 6; // __launch_bounds__ min blocks of k_connect (BDPT_CONNECT_MINB, tuning only)
   int traits = 0;       // BDPT_TRAIT_* of the uploaded scene
+  int point_lights = 0; // the uploaded scene has a point light
   int spec = 7;         // which kernels may use their trait-specialised build: 1 walk, 2 connect, 4 shadow (BDPT_SPEC, tuning only)
   // batch size cap (samples) and its memory budget (BDPT_BATCH_LOG2, BDPT_BATCH_GIB).  The persistent kernels end
   // with a tail of long paths; at 2^24 samples per batch that tail is ~1 % of the step (2^22: ~4 %), and 48 of the
@@ -201,7 +202,7 @@ cudaEvent_t get_event(BdptContext* ctx, size_t i) {
 
 void fill_job(BdptContext* ctx, const BdptRenderParams* p, Job* J) {
   memset(J, 0, sizeof(Job));
-  J->sc = ctx->sc; J->cam = ctx->cam;
+  J->sc = ctx->sc; J->cam = ctx->cam; J->point_lights = ctx->point_lights;
   J->v0 = ctx->v0; J->v1 = ctx->v1; J->v2 = ctx->v2; J->v3 = ctx->v3; J->counts = ctx->counts;
   J->q0 = ctx->q0; J->q1 = ctx->q1; J->q2 = ctx->q2; J->qctr = ctx->qctr; J->qcap = (unsigned int)ctx->cap_q;
   J->acc_eye = ctx->acc_eye; J->acc_light = ctx->acc_light; J->stats = ctx->d_stats; J->dbg = nullptr;
@@ -249,7 +250,15 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
       default: k_walk_pt<16, 8, 6, 0><<<g, threads, shm, ctx->stream>>>(J); break;
     }
   }
-  else k_walk<<<(2 * J.B + threads - 1) / threads, threads, 0, ctx->stream>>>(J);
+  else {
+    const unsigned g = (unsigned)((2 * J.B + threads - 1) / threads);
+    switch ((ctx->spec & 1) ? ctx->traits : 0) {
+      case 1: k_walk<1><<<g, threads, 0, ctx->stream>>>(J); break;
+      case 2: k_walk<2><<<g, threads, 0, ctx->stream>>>(J); break;
+      case 3: k_walk<3><<<g, threads, 0, ctx->stream>>>(J); break;
+      default: k_walk<0><<<g, threads, 0, ctx->stream>>>(J); break;
+    }
+  }
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 1), ctx->stream);
   const unsigned cgrid = (unsigned)((J.B + threads - 1) / threads) * (unsigned)(J.m + 1);
   const bool lambert = !TRACE && (ctx->spec & 2) && (ctx->traits & BDPT_TRAIT_LAMBERT);
@@ -282,7 +291,8 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
       k_shadow_pt<8><<<ctx->sm_count * c, threads, shm, ctx->stream>>>(J);
     }
   }
-  else k_shadow<<<ctx->sm_count * 8, threads, 0, ctx->stream>>>(J);
+  else if ((ctx->spec & 4) && (ctx->traits & BDPT_TRAIT_TRIS)) k_shadow<BDPT_TRAIT_TRIS><<<ctx->sm_count * 8, threads, 0, ctx->stream>>>(J);
+  else k_shadow<0><<<ctx->sm_count * 8, threads, 0, ctx->stream>>>(J);
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 3), ctx->stream);
   ctx->stats.kernel_launches += 3;
   CK(cudaGetLastError());
@@ -487,6 +497,8 @@ int bdpt_upload_scene(BdptContext* ctx, const BdptCamera* camera, const BdptMate
   for (uint32_t i = 0; i < n_materials; i++)
     if (materials[i].type != BDPT_MAT_DIFFUSE && materials[i].type != BDPT_MAT_EMISSION) { traits &= ~BDPT_TRAIT_LAMBERT; break; }
   ctx->traits = traits;
+  ctx->point_lights = 0;
+  for (uint32_t i = 0; i < n_lights; i++) if (lights[i].type == BDPT_LIGHT_POINT) ctx->point_lights = 1;
   ctx->cam_base = *camera;
   ctx->have_scene = true;
   if (ctx->W > 0) make_dcamera(ctx->cam_base, ctx->W, ctx->H, &ctx->cam);

@@ -56,6 +56,7 @@ struct Job {
   int ntop;                   // BVH nodes staged in shared memory by the persistent kernels
   int no_mis;                 // weight 1 for every strategy: the reference's own debug switch (bidirection.cpp:124-126)
   int only_t, only_s;
+  int point_lights;           // the scene has a point light: light-image splats collide (shadow_splat)
   int single_x, single_y;     // >= 0: the job is this one pixel (trace mode)
 };
 
@@ -80,6 +81,7 @@ __device__ inline bool decode_sample(const Job& J, unsigned long long g, int* x,
 __device__ inline float clampS(float s) { return fminf(s, 1e30f); }
 
 // ---------------------------------------------------------------------------------------- walk
+template <int TR = 0>
 __global__ void __launch_bounds__(128) k_walk(const Job J) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * J.B) return;
@@ -122,14 +124,14 @@ __global__ void __launch_bounds__(128) k_walk(const Job J) {
 
   unsigned int nrays = 0;
   for (int j = 2; j <= J.m + 1; j++) {
-    Hit h = traverse<false>(sc, o, d, tmin, tmax);
+    Hit h = traverse<false, TR>(sc, o, d, tmin, tmax);
     nrays++;
     if (h.leaf < 0) break;
     f3 n, hit_p; int prim, mat;
-    finish_hit(sc, h, o, d, &n, &prim, &mat, &hit_p);
+    finish_hit<TR>(sc, h, o, d, &n, &prim, &mat, &hit_p);
     const Frame fr = make_frame(n);
     const f3 w_out = fr.to_local(-d);
-    const Mat M = load_mat(sc, mat);
+    const Mat M = load_mat<TR>(sc, mat);
     f3 wi; float pdf;
     const f3 f = bsdf_sample_f(M, w_out, &wi, &pdf, rng);
     const f3 wi_world = normalized(fr.to_world(wi));
@@ -428,8 +430,34 @@ __global__ void __launch_bounds__(128, MINB) k_connect(const Job J) {
 }
 
 // -------------------------------------------------------------------------------------- shadow
-// Persistent warps: each warp claims 32 queue entries with one atomic, traces them any-hit and
-// splats the survivors.  Grid = (resident CTAs per SM) x 148.
+// Adds unoccluded connections to their pixels.  Called by a converged set of lanes (`mask`, every lane of it holds
+// queue entry idx).  In scenes with a point light (J.point_lights) the t=1, s=1 connection of EVERY sample is the same
+// ray and lands on the same pixel of the light image; 38 M same-address atomics per batch took 57 of CBempty's
+// 60 ms.  There, lanes of the set that splat the same light-image pixel are summed first and their leader issues the
+// three atomics.
+__device__ inline void shadow_splat(const Job& J, unsigned mask, unsigned idx) {
+  float4 b = J.q1[idx], c = J.q2[idx];
+  const unsigned int tg = __float_as_uint(b.w);
+  float sx = c.x, sy = c.y, sz = c.z;
+  if (J.point_lights) {
+    const unsigned li = __ballot_sync(mask, (tg & 0x80000000u) != 0u);
+    if (tg & 0x80000000u) {
+      const unsigned peers = __match_any_sync(li, tg);
+      if (peers & (peers - 1u)) {   // more than this lane
+        sx = sy = sz = 0.f;
+        for (unsigned rem = peers; rem; rem &= rem - 1u) {
+          const int src = __ffs(rem) - 1;
+          sx += __shfl_sync(peers, c.x, src); sy += __shfl_sync(peers, c.y, src); sz += __shfl_sync(peers, c.z, src);
+        }
+        if ((int)(threadIdx.x & 31) != __ffs(peers) - 1) return;
+      }
+    }
+  }
+  float* px = ((tg & 0x80000000u) ? J.acc_light : J.acc_eye) + 3 * (size_t)(tg & 0x7fffffffu);
+  atomicAdd(px + 0, sx); atomicAdd(px + 1, sy); atomicAdd(px + 2, sz);
+}
+
+template <int TR = 0>
 __global__ void __launch_bounds__(128) k_shadow(const Job J) {
   const unsigned int n = min(J.qctr[0], J.qcap);
   const int lane = threadIdx.x & 31;
@@ -442,14 +470,10 @@ __global__ void __launch_bounds__(128) k_shadow(const Job J) {
     unsigned int idx = base + lane;
     if (idx < n) {
       float4 a = J.q0[idx], b = J.q1[idx];
-      Hit h = traverse<true>(J.sc, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), BDPT_EPS_F, a.w);
+      Hit h = traverse<true, TR>(J.sc, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), BDPT_EPS_F, a.w);
       traced++;
-      if (h.leaf < 0) {
-        float4 c = J.q2[idx];
-        unsigned int tg = __float_as_uint(b.w);
-        float* px = ((tg & 0x80000000u) ? J.acc_light : J.acc_eye) + 3 * (size_t)(tg & 0x7fffffffu);
-        atomicAdd(px + 0, c.x); atomicAdd(px + 1, c.y); atomicAdd(px + 2, c.z);
-      }
+      const unsigned clear = __ballot_sync(__activemask(), h.leaf < 0);
+      if (h.leaf < 0) shadow_splat(J, clear, idx);
     }
   }
   unsigned int tot = __reduce_add_sync(0xffffffffu, traced);
@@ -494,14 +518,6 @@ __device__ inline void stage_top_nodes(const Job& J, uint4* top) {
   __syncthreads();
 }
 
-// Adds an unoccluded connection to its pixel (queue entry idx).
-__device__ inline void shadow_splat(const Job& J, unsigned idx) {
-  float4 b = J.q1[idx], c = J.q2[idx];
-  unsigned int tg = __float_as_uint(b.w);
-  float* px = ((tg & 0x80000000u) ? J.acc_light : J.acc_eye) + 3 * (size_t)(tg & 0x7fffffffu);
-  atomicAdd(px + 0, c.x); atomicAdd(px + 1, c.y); atomicAdd(px + 2, c.z);
-}
-
 template <int MINB, int TR = 0>
 __global__ void __launch_bounds__(128, MINB) k_shadow_pt(const Job J) {
   extern __shared__ uint4 top[];
@@ -518,8 +534,9 @@ __global__ void __launch_bounds__(128, MINB) k_shadow_pt(const Job J) {
 #pragma unroll 1
   for (;;) {
     const unsigned idle = __ballot_sync(0xffffffffu, !active);
-    if (__popc(__ballot_sync(0xffffffffu, pend != BDPT_NONE)) >= 16) {
-      if (pend != BDPT_NONE) { shadow_splat(J, pend); pend = BDPT_NONE; }
+    const unsigned parked = __ballot_sync(0xffffffffu, pend != BDPT_NONE);
+    if (__popc(parked) >= 16) {
+      if (pend != BDPT_NONE) { shadow_splat(J, parked, pend); pend = BDPT_NONE; }
     }
     if (!wf.exhausted && (__popc(idle) >= 4 || idle == 0xffffffffu)) {
       unsigned my = warp_fetch(J.qctr + 1, n, 256u, !active, wf);
@@ -537,12 +554,13 @@ __global__ void __launch_bounds__(128, MINB) k_shadow_pt(const Job J) {
       traced++;
       active = false;
       if (T.hit.leaf < 0) {
-        if (pend != BDPT_NONE) shadow_splat(J, pend);   // the slot is taken: this lane cannot wait for the warp
+        if (pend != BDPT_NONE) shadow_splat(J, 1u << (threadIdx.x & 31), pend);   // the slot is taken: this lane cannot wait
         pend = idx;
       }
     }
   }
-  if (pend != BDPT_NONE) shadow_splat(J, pend);
+  const unsigned left = __ballot_sync(0xffffffffu, pend != BDPT_NONE);
+  if (pend != BDPT_NONE) shadow_splat(J, left, pend);
   unsigned int tot = __reduce_add_sync(0xffffffffu, traced);
   if ((threadIdx.x & 31) == 0 && tot) atomicAdd(J.stats + 1, (unsigned long long)tot);
 }
