@@ -8,7 +8,11 @@
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <deque>
+#include <thread>
 
 namespace bdpt {
 namespace {
@@ -37,8 +41,11 @@ struct Builder {
   const std::vector<BuildPrim>& prims;
   std::vector<uint32_t> idx;
   std::vector<float> cent;  // 3 per prim
-  std::vector<BNode> bn;
+  std::vector<BNode> bn;    // preallocated (2n - 1 nodes at most): subtrees are built by several threads
+  std::atomic<int> next_node{0};
+  std::atomic<int> spare_threads{0};
   static constexpr int kBins = 16;
+  static constexpr int kParallelMin = 4096;   // subtrees smaller than this are not worth a thread
   int kMaxLeaf = 3;        // primitives per leaf child (<= 3: the node's meta byte counts them in unary)
   float kTravCost = 0.5f;  // SAH cost of one more traversal step relative to one primitive test
 
@@ -49,9 +56,52 @@ struct Builder {
       idx[i] = (uint32_t)i;
       for (int a = 0; a < 3; a++) cent[3 * i + a] = 0.5f * (p[i].lo[a] + p[i].hi[a]);
     }
-    bn.reserve(p.size() * 2 + 1);
+    bn.resize(p.size() * 2 + 1);
     if (const char* e = getenv("BDPT_BVH_LEAF")) kMaxLeaf = std::max(1, std::min(3, atoi(e)));   // tuning knobs
     if (const char* e = getenv("BDPT_BVH_CT")) kTravCost = (float)atof(e);
+    int hw = (int)std::thread::hardware_concurrency();
+    if (const char* e = getenv("BDPT_BVH_THREADS")) hw = atoi(e);
+    spare_threads = std::max(0, std::min(hw, 16) - 1);
+  }
+
+  // Nodes of at most kExactMax primitives: exact sweep SAH over the centroid order of each axis.  (Resetting and
+  // sweeping 3 x 16 bins for every one of the ~2n small nodes was 80 % of the build time.)
+  static constexpr int kExactMax = 12;
+  int build_small(int me, int first, int count, const Box& cb) {
+    uint32_t ord[kExactMax], best_ord[kExactMax];
+    float right_area[kExactMax];
+    float best_cost = FLT_MAX; int best_split = -1;
+    for (int a = 0; a < 3; a++) {
+      if (!(cb.hi[a] - cb.lo[a] > 0.f)) continue;
+      for (int i = 0; i < count; i++) ord[i] = idx[first + i];
+      // insertion sort by centroid (stable: ties keep the incoming order)
+      for (int i = 1; i < count; i++) {
+        uint32_t v = ord[i]; float c = cent[3 * v + a]; int j = i - 1;
+        while (j >= 0 && cent[3 * ord[j] + a] > c) { ord[j + 1] = ord[j]; j--; }
+        ord[j + 1] = v;
+      }
+      Box acc; acc.reset();
+      for (int i = count - 1; i >= 1; i--) { acc.grow(prims[ord[i]].lo, prims[ord[i]].hi); right_area[i] = acc.half_area(); }
+      acc.reset();
+      for (int i = 1; i < count; i++) {   // left = ord[0..i), right = ord[i..count)
+        acc.grow(prims[ord[i - 1]].lo, prims[ord[i - 1]].hi);
+        float cost = acc.half_area() * i + right_area[i] * (count - i);
+        if (cost < best_cost) { best_cost = cost; best_split = i; for (int k = 0; k < count; k++) best_ord[k] = ord[k]; }
+      }
+    }
+    const float area = bn[me].box.half_area();
+    if (count <= kMaxLeaf) {
+      float leaf_cost = area * count;
+      float split_cost = best_split < 0 ? FLT_MAX : kTravCost * area + best_cost;
+      if (leaf_cost <= split_cost) return me;
+    }
+    int mid;
+    if (best_split < 0) mid = first + count / 2;   // identical centroids: split by index
+    else { for (int k = 0; k < count; k++) idx[first + k] = best_ord[k]; mid = first + best_split; }
+    const int l = build(first, mid - first);
+    const int r = build(mid, first + count - mid);
+    bn[me].left = l; bn[me].right = r;
+    return me;
   }
 
   int build(int first, int count) {
@@ -65,28 +115,38 @@ struct Builder {
       cb.grow(c, c);
     }
     n.first = first; n.count = count;
-    int me = (int)bn.size();
-    bn.push_back(n);
+    const int me = next_node.fetch_add(1);
+    bn[me] = n;
     if (count == 1) return me;
 
-    // binned SAH over the three axes
+    if (count <= kExactMax) return build_small(me, first, count, cb);
+
+    // binned SAH over the three axes, one pass over the primitives
     float best_cost = FLT_MAX; int best_axis = -1, best_split = -1;
+    Box bb[3][kBins]; int bc[3][kBins]; float kk[3]; bool use[3];
     for (int a = 0; a < 3; a++) {
       float ext = cb.hi[a] - cb.lo[a];
-      if (!(ext > 0.f)) continue;
-      Box bb[kBins]; int bc[kBins];
-      for (int b = 0; b < kBins; b++) { bb[b].reset(); bc[b] = 0; }
-      float k = kBins * (1.f - 1e-6f) / ext;
-      for (int i = first; i < first + count; i++) {
-        int b = std::min(kBins - 1, std::max(0, (int)((cent[3 * idx[i] + a] - cb.lo[a]) * k)));
-        bb[b].grow(prims[idx[i]].lo, prims[idx[i]].hi); bc[b]++;
+      use[a] = ext > 0.f;
+      kk[a] = use[a] ? kBins * (1.f - 1e-6f) / ext : 0.f;
+      for (int b = 0; b < kBins; b++) { bb[a][b].reset(); bc[a][b] = 0; }
+    }
+    for (int i = first; i < first + count; i++) {
+      const uint32_t id = idx[i];
+      const BuildPrim& p = prims[id];
+      for (int a = 0; a < 3; a++) {
+        if (!use[a]) continue;
+        int b = std::min(kBins - 1, std::max(0, (int)((cent[3 * id + a] - cb.lo[a]) * kk[a])));
+        bb[a][b].grow(p.lo, p.hi); bc[a][b]++;
       }
+    }
+    for (int a = 0; a < 3; a++) {
+      if (!use[a]) continue;
       float la[kBins]; int lc[kBins];
       Box acc; acc.reset(); int cnt = 0;
-      for (int b = 0; b < kBins; b++) { acc.grow(bb[b]); cnt += bc[b]; la[b] = acc.half_area(); lc[b] = cnt; }
+      for (int b = 0; b < kBins; b++) { acc.grow(bb[a][b]); cnt += bc[a][b]; la[b] = acc.half_area(); lc[b] = cnt; }
       acc.reset(); cnt = 0;
       for (int b = kBins - 1; b >= 1; b--) {
-        acc.grow(bb[b]); cnt += bc[b];
+        acc.grow(bb[a][b]); cnt += bc[a][b];
         if (lc[b - 1] == 0 || cnt == 0) continue;
         float cost = la[b - 1] * lc[b - 1] + acc.half_area() * cnt;
         if (cost < best_cost) { best_cost = cost; best_axis = a; best_split = b; }
@@ -102,8 +162,7 @@ struct Builder {
     if (best_axis < 0) {
       mid = first + count / 2;  // identical centroids: split by index
     } else {
-      float ext = cb.hi[best_axis] - cb.lo[best_axis];
-      float k = kBins * (1.f - 1e-6f) / ext;
+      float k = kk[best_axis];
       float lo = cb.lo[best_axis];
       auto it = std::partition(idx.begin() + first, idx.begin() + first + count, [&](uint32_t id) {
         int b = std::min(kBins - 1, std::max(0, (int)((cent[3 * id + best_axis] - lo) * k)));
@@ -112,8 +171,21 @@ struct Builder {
       mid = (int)(it - idx.begin());
       if (mid == first || mid == first + count) mid = first + count / 2;
     }
-    int l = build(first, mid - first);
-    int r = build(mid, first + count - mid);
+    // the two halves touch disjoint ranges of idx and claim their nodes from the atomic counter: the left one may
+    // run on another thread.  The tree does not depend on which thread built what (node numbers do; the collapse
+    // below only follows left / right links).
+    int l, r;
+    const int nl = mid - first, nr = first + count - mid;
+    if (std::min(nl, nr) >= kParallelMin && spare_threads.fetch_sub(1) > 0) {
+      std::thread t([&] { l = build(first, nl); });
+      r = build(mid, nr);
+      t.join();
+      spare_threads.fetch_add(1);
+    } else {
+      if (std::min(nl, nr) >= kParallelMin) spare_threads.fetch_add(1);   // undo the failed claim
+      l = build(first, nl);
+      r = build(mid, nr);
+    }
     bn[me].left = l; bn[me].right = r;
     return me;
   }
@@ -126,8 +198,11 @@ inline uint32_t fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 void build_bvh8(const std::vector<BuildPrim>& prims, Bvh8* out) {
   out->nodes.clear(); out->prim_order.clear(); out->max_depth = 1;
   if (prims.empty()) { out->nodes.assign(20, 0u); return; }
+  auto T0 = std::chrono::steady_clock::now();
   Builder B(prims);
+  auto T1 = std::chrono::steady_clock::now();
   int root = B.build(0, (int)prims.size());
+  auto T2 = std::chrono::steady_clock::now();
 
   struct Item { int wide; int bnode; uint32_t depth; };
   std::deque<Item> queue;
@@ -242,6 +317,11 @@ void build_bvh8(const std::vector<BuildPrim>& prims, Bvh8* out) {
     auto pack4 = [](const uint8_t* b) { return (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24); };
     w[6] = pack4(meta); w[7] = pack4(meta + 4);
     for (int r = 0; r < 6; r++) { w[8 + 2 * r] = pack4(q[r]); w[9 + 2 * r] = pack4(q[r] + 4); }
+  }
+  if (getenv("BDPT_BVH_TIMING")) {
+    auto T3 = std::chrono::steady_clock::now();
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    fprintf(stderr, "bvh8: setup %.1f ms, sah %.1f ms, collapse+quantise %.1f ms\n", ms(T0, T1), ms(T1, T2), ms(T2, T3));
   }
 }
 
