@@ -47,7 +47,7 @@ struct Builder {
   static constexpr int kBins = 16;
   static constexpr int kParallelMin = 4096;   // subtrees smaller than this are not worth a thread
   int kMaxLeaf = 3;        // primitives per leaf child (<= 3: the node's meta byte counts them in unary)
-  float kTravCost = 0.5f;  // SAH cost of one more traversal step relative to one primitive test
+  float kPrimCost = 0.4f;  // SAH cost of one primitive test relative to one visit of an 8-wide node
 
   explicit Builder(const std::vector<BuildPrim>& p) : prims(p) {
     idx.resize(p.size());
@@ -58,7 +58,7 @@ struct Builder {
     }
     bn.resize(p.size() * 2 + 1);
     if (const char* e = getenv("BDPT_BVH_LEAF")) kMaxLeaf = std::max(1, std::min(3, atoi(e)));   // tuning knobs
-    if (const char* e = getenv("BDPT_BVH_CT")) kTravCost = (float)atof(e);
+    if (const char* e = getenv("BDPT_BVH_CP")) kPrimCost = (float)atof(e);
     int hw = (int)std::thread::hardware_concurrency();
     if (const char* e = getenv("BDPT_BVH_THREADS")) hw = atoi(e);
     spare_threads = std::max(0, std::min(hw, 16) - 1);
@@ -88,12 +88,6 @@ struct Builder {
         float cost = acc.half_area() * i + right_area[i] * (count - i);
         if (cost < best_cost) { best_cost = cost; best_split = i; for (int k = 0; k < count; k++) best_ord[k] = ord[k]; }
       }
-    }
-    const float area = bn[me].box.half_area();
-    if (count <= kMaxLeaf) {
-      float leaf_cost = area * count;
-      float split_cost = best_split < 0 ? FLT_MAX : kTravCost * area + best_cost;
-      if (leaf_cost <= split_cost) return me;
     }
     int mid;
     if (best_split < 0) mid = first + count / 2;   // identical centroids: split by index
@@ -152,12 +146,6 @@ struct Builder {
         if (cost < best_cost) { best_cost = cost; best_axis = a; best_split = b; }
       }
     }
-    float area = n.box.half_area();
-    if (count <= kMaxLeaf) {
-      float leaf_cost = area * count;
-      float split_cost = best_axis < 0 ? FLT_MAX : kTravCost * area + best_cost;
-      if (leaf_cost <= split_cost) return me;
-    }
     int mid;
     if (best_axis < 0) {
       mid = first + count / 2;  // identical centroids: split by index
@@ -204,6 +192,63 @@ void build_bvh8(const std::vector<BuildPrim>& prims, Bvh8* out) {
   int root = B.build(0, (int)prims.size());
   auto T2 = std::chrono::steady_clock::now();
 
+  // ---- SAH-optimal collapse of the binary tree into 8-wide nodes (Ylitie, Karras, Laine 2017, section 3.2).
+  // C(n, i): cheapest way to represent the subtree of binary node n as at most i roots (i = 1..7).  One root is
+  // either a leaf child (<= kMaxLeaf primitives) or a wide node whose <= 8 children are the roots its two subtrees
+  // are distributed into:  C(n,1) = min(A_n P_n c_p,  A_n + min_k C(l,k) + C(r,8-k)),
+  // C(n,i) = min(C(n,i-1), min_k C(l,k) + C(r,i-k)).  The greedy "open the largest child" collapse this replaces
+  // left the average node half empty (4.1 of 8 slots on CBbunny, a quarter of the nodes with two children).
+  const int nbn = B.next_node.load();
+  std::vector<float> C((size_t)nbn * 8, FLT_MAX);          // C[n*8 + i], i = 1..7
+  std::vector<uint8_t> split((size_t)nbn * 9, 0);          // split[n*9 + j], j = 2..8: roots given to the left subtree; 0 = "use j-1 roots"
+  std::vector<uint8_t> is_leaf((size_t)nbn, 0);            // the one-root form of n is a leaf child
+  {
+    std::vector<int> order; order.reserve(nbn);
+    std::vector<int> st; st.push_back(root);
+    while (!st.empty()) { int n = st.back(); st.pop_back(); order.push_back(n); if (B.bn[n].left >= 0) { st.push_back(B.bn[n].left); st.push_back(B.bn[n].right); } }
+    for (size_t oi = order.size(); oi-- > 0;) {            // children before parents
+      const int n = order[oi];
+      const BNode& bnode = B.bn[n];
+      const float A = bnode.box.half_area();
+      float* c = &C[(size_t)n * 8];
+      if (bnode.left < 0) {                                // a single primitive
+        for (int i = 1; i <= 7; i++) c[i] = A * B.kPrimCost;
+        is_leaf[n] = 1;
+        continue;
+      }
+      const float* cl = &C[(size_t)bnode.left * 8];
+      const float* cr = &C[(size_t)bnode.right * 8];
+      uint8_t* sp = &split[(size_t)n * 9];
+      float dist[9];
+      for (int j = 2; j <= 8; j++) {
+        float best = FLT_MAX; int bk = 1;
+        for (int k = std::max(1, j - 7); k <= std::min(7, j - 1); k++) {
+          float v = cl[k] + cr[j - k];
+          if (v < best) { best = v; bk = k; }
+        }
+        dist[j] = best; sp[j] = (uint8_t)bk;
+      }
+      const float c_leaf = bnode.count <= B.kMaxLeaf ? A * (float)bnode.count * B.kPrimCost : FLT_MAX;
+      const float c_int = dist[8] + A;
+      if (c_leaf <= c_int) { c[1] = c_leaf; is_leaf[n] = 1; } else { c[1] = c_int; }
+      for (int i = 2; i <= 7; i++) {
+        if (dist[i] < c[i - 1]) c[i] = dist[i];
+        else { c[i] = c[i - 1]; sp[i] = 0; }
+      }
+    }
+  }
+  // the roots that represent binary node n with a budget of i
+  struct Collect {
+    const Builder& B; const std::vector<uint8_t>& split;
+    void run(int n, int i, int* out, int& nout) const {
+      while (i > 1 && B.bn[n].left >= 0 && split[(size_t)n * 9 + i] == 0) i--;
+      if (i == 1 || B.bn[n].left < 0) { out[nout++] = n; return; }
+      const int k = split[(size_t)n * 9 + i];
+      run(B.bn[n].left, k, out, nout);
+      run(B.bn[n].right, i - k, out, nout);
+    }
+  } collect{B, split};
+
   struct Item { int wide; int bnode; uint32_t depth; };
   std::deque<Item> queue;
   out->nodes.assign(20, 0u);
@@ -212,22 +257,12 @@ void build_bvh8(const std::vector<BuildPrim>& prims, Bvh8* out) {
     Item it = queue.front(); queue.pop_front();
     out->max_depth = std::max(out->max_depth, it.depth);
     const BNode& top = B.bn[it.bnode];
-    // collapse: expand the largest internal child until 8 children
     int ch[8]; int nch = 0;
-    if (top.left < 0) { ch[nch++] = it.bnode; }
-    else { ch[nch++] = top.left; ch[nch++] = top.right; }
-    while (nch < 8) {
-      int pick = -1; float best = -1.f;
-      for (int i = 0; i < nch; i++) {
-        const BNode& c = B.bn[ch[i]];
-        if (c.left < 0) continue;
-        float a = c.box.half_area();
-        if (a > best) { best = a; pick = i; }
-      }
-      if (pick < 0) break;
-      const BNode& c = B.bn[ch[pick]];
-      int l = c.left, r = c.right;
-      ch[pick] = l; ch[nch++] = r;
+    if (top.left < 0) { ch[nch++] = it.bnode; }            // a one-primitive scene
+    else {
+      const int k = split[(size_t)it.bnode * 9 + 8];
+      collect.run(top.left, k, ch, nch);
+      collect.run(top.right, 8 - k, ch, nch);
     }
     // octant slot assignment (greedy maximum of centroid offset . slot direction)
     float nc[3];
@@ -293,7 +328,7 @@ void build_bvh8(const std::vector<BuildPrim>& prims, Bvh8* out) {
         while (qhi < 255 && p[a] + (float)qhi * scale[a] < cn.box.hi[a] + slack[a]) qhi++;
         q[a][s] = (uint8_t)qlo; q[3 + a][s] = (uint8_t)qhi;
       }
-      if (cn.left >= 0) {
+      if (!is_leaf[ch[c]]) {
         imask |= 1u << s;
         meta[s] = (uint8_t)(0x20 | (24 + s));
       } else {
