@@ -44,7 +44,8 @@ struct Builder {
   std::vector<BNode> bn;    // preallocated (2n - 1 nodes at most): subtrees are built by several threads
   std::atomic<int> next_node{0};
   std::atomic<int> spare_threads{0};
-  static constexpr int kBins = 16;
+  static constexpr int kMaxBins = 64;
+  int kBins = 16;          // SAH bins per axis (BDPT_BVH_BINS, tuning only)
   static constexpr int kParallelMin = 4096;   // subtrees smaller than this are not worth a thread
   int kMaxLeaf = 3;        // primitives per leaf child (<= 3: the node's meta byte counts them in unary)
   float kPrimCost = 0.4f;  // SAH cost of one primitive test relative to one visit of an 8-wide node
@@ -59,6 +60,7 @@ struct Builder {
     bn.resize(p.size() * 2 + 1);
     if (const char* e = getenv("BDPT_BVH_LEAF")) kMaxLeaf = std::max(1, std::min(3, atoi(e)));   // tuning knobs
     if (const char* e = getenv("BDPT_BVH_CP")) kPrimCost = (float)atof(e);
+    if (const char* e = getenv("BDPT_BVH_BINS")) kBins = std::max(2, std::min(kMaxBins, atoi(e)));
     int hw = (int)std::thread::hardware_concurrency();
     if (const char* e = getenv("BDPT_BVH_THREADS")) hw = atoi(e);
     spare_threads = std::max(0, std::min(hw, 16) - 1);
@@ -117,7 +119,7 @@ struct Builder {
 
     // binned SAH over the three axes, one pass over the primitives
     float best_cost = FLT_MAX; int best_axis = -1, best_split = -1;
-    Box bb[3][kBins]; int bc[3][kBins]; float kk[3]; bool use[3];
+    Box bb[3][kMaxBins]; int bc[3][kMaxBins]; float kk[3]; bool use[3];
     for (int a = 0; a < 3; a++) {
       float ext = cb.hi[a] - cb.lo[a];
       use[a] = ext > 0.f;
@@ -135,7 +137,7 @@ struct Builder {
     }
     for (int a = 0; a < 3; a++) {
       if (!use[a]) continue;
-      float la[kBins]; int lc[kBins];
+      float la[kMaxBins]; int lc[kMaxBins];
       Box acc; acc.reset(); int cnt = 0;
       for (int b = 0; b < kBins; b++) { acc.grow(bb[a][b]); cnt += bc[a][b]; la[b] = acc.half_area(); lc[b] = cnt; }
       acc.reset(); cnt = 0;
@@ -276,17 +278,29 @@ void build_bvh8(const std::vector<BuildPrim>& prims, Bvh8* out) {
         cost[c][s] = ((s & 1) ? off[0] : -off[0]) + ((s & 2) ? off[1] : -off[1]) + ((s & 4) ? off[2] : -off[2]);
     }
     int slot_child[8]; for (int s = 0; s < 8; s++) slot_child[s] = -1;
-    bool cdone[8] = {false, false, false, false, false, false, false, false};
-    for (int k = 0; k < nch; k++) {
-      float best = -FLT_MAX; int bc = -1, bs = -1;
-      for (int c = 0; c < nch; c++) {
-        if (cdone[c]) continue;
-        for (int s = 0; s < 8; s++) {
-          if (slot_child[s] >= 0) continue;
-          if (cost[c][s] > best) { best = cost[c][s]; bc = c; bs = s; }
-        }
+    {
+      // optimal assignment (maximum total of cost[child][slot]): Hungarian method on the 8 x 8 matrix, absent
+      // children padded with zero rows
+      const int N = 8;
+      double a[N + 1][N + 1];
+      for (int i = 1; i <= N; i++) for (int j = 1; j <= N; j++) a[i][j] = i <= nch ? -(double)cost[i - 1][j - 1] : 0.0;
+      double u[N + 1] = {0}, v[N + 1] = {0}; int pm[N + 1] = {0}, way[N + 1] = {0};
+      for (int i = 1; i <= N; i++) {
+        pm[0] = i; int j0 = 0; double minv[N + 1]; bool used[N + 1];
+        for (int j = 0; j <= N; j++) { minv[j] = 1e300; used[j] = false; }
+        do {
+          used[j0] = true; int i0 = pm[j0], j1 = 0; double delta = 1e300;
+          for (int j = 1; j <= N; j++) if (!used[j]) {
+            double cur = a[i0][j] - u[i0] - v[j];
+            if (cur < minv[j]) { minv[j] = cur; way[j] = j0; }
+            if (minv[j] < delta) { delta = minv[j]; j1 = j; }
+          }
+          for (int j = 0; j <= N; j++) if (used[j]) { u[pm[j]] += delta; v[j] -= delta; } else minv[j] -= delta;
+          j0 = j1;
+        } while (pm[j0] != 0);
+        do { int j1 = way[j0]; pm[j0] = pm[j1]; j0 = j1; } while (j0);
       }
-      cdone[bc] = true; slot_child[bs] = bc;
+      for (int j = 1; j <= N; j++) if (pm[j] >= 1 && pm[j] <= nch) slot_child[j - 1] = pm[j] - 1;
     }
     // quantisation grid.  Every decoded plane keeps at least 1/64 of a quantum of slack to the box it
     // bounds (the grid origin sits 1/32 quantum below the node's min corner): the traversal decodes a
