@@ -111,6 +111,9 @@ struct DScene {
   uint32_t qbias_bits;
 };
 
+// 1/x by the SFU alone (MUFU.RCP, <= 1 ulp on normal inputs; denormals flush): __fdividef(1, x) adds a range fix-up
+__device__ inline float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 __device__ inline float4 ldg4(const float4* p) { return __ldg(p); }
 __device__ inline uint4 ldg4(const uint4* p) { return __ldg(p); }
 

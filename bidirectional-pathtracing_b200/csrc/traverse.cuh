@@ -44,7 +44,7 @@ __device__ inline bool intersect_prim(const float4* __restrict__ prims, int k, f
     f3 e1 = mk3(b.x, b.y, b.z), e2 = mk3(c.x, c.y, c.z);
     f3 s = o - mk3(a.x, a.y, a.z);
     f3 s1 = cross(d, e2), s2 = cross(s, e1);
-    float inv = __fdividef(1.0f, dot(s1, e1));   // MUFU.RCP, <= 2 ulp: the winner is re-intersected in fp64 (finish_hit)
+    float inv = rcp_fast(dot(s1, e1));   // the winner is re-intersected in fp64 (finish_hit)
     float t = dot(s2, e2) * inv, b1 = dot(s1, s) * inv, b2 = dot(s2, d) * inv;
     if (t >= tmin && t <= tmax && b1 >= 0.f && b2 >= 0.f && b1 + b2 <= 1.f) {
       tmax = t; b1o = b1; b2o = b2;
@@ -83,9 +83,9 @@ struct Trav {
     hit.t = tmax_; hit.leaf = -1; hit.b1 = 0.f; hit.b2 = 0.f;
     oct = (d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u);
     // MUFU.RCP (<= 2 ulp): the reciprocals only feed the box cull, whose slack factor below covers them
-    idir.x = __fdividef(1.0f, fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x));
-    idir.y = __fdividef(1.0f, fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y));
-    idir.z = __fdividef(1.0f, fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z));
+    idir.x = rcp_fast(fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x));
+    idir.y = rcp_fast(fabsf(d.y) > 1e-20f ? d.y : copysignf(1e-20f, d.y));
+    idir.z = rcp_fast(fabsf(d.z) > 1e-20f ? d.z : copysignf(1e-20f, d.z));
     sp = 0;
     group = make_uint2(0u, 0x80000000u);  // root: node 0, top priority bit
   }
