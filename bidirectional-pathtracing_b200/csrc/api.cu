@@ -247,6 +247,8 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
       case 1: k_walk_pt<16, 8, 6, 1><<<g, threads, shm, ctx->stream>>>(J); break;
       case 2: k_walk_pt<16, 8, 6, 2><<<g, threads, shm, ctx->stream>>>(J); break;
       case 3: k_walk_pt<16, 8, 6, 3><<<g, threads, shm, ctx->stream>>>(J); break;
+      case 4: k_walk_pt<16, 8, 6, 4><<<g, threads, shm, ctx->stream>>>(J); break;
+      case 5: k_walk_pt<16, 8, 6, 5><<<g, threads, shm, ctx->stream>>>(J); break;
       default: k_walk_pt<16, 8, 6, 0><<<g, threads, shm, ctx->stream>>>(J); break;
     }
   }
@@ -256,6 +258,8 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
       case 1: k_walk<1><<<g, threads, 0, ctx->stream>>>(J); break;
       case 2: k_walk<2><<<g, threads, 0, ctx->stream>>>(J); break;
       case 3: k_walk<3><<<g, threads, 0, ctx->stream>>>(J); break;
+      case 4: k_walk<4><<<g, threads, 0, ctx->stream>>>(J); break;
+      case 5: k_walk<5><<<g, threads, 0, ctx->stream>>>(J); break;
       default: k_walk<0><<<g, threads, 0, ctx->stream>>>(J); break;
     }
   }
@@ -264,6 +268,8 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
   const bool lambert = !TRACE && (ctx->spec & 2) && (ctx->traits & BDPT_TRAIT_LAMBERT);
   // The Lambert build needs 96 registers unspilled and runs best that way (5 CTAs/SM); forced to 80 registers it is
   // slower than the generic build at 80, which tolerates its spills (measured: 6.3 / 9.7 / 7.2 ms per 2^24 samples).
+  // A no-microfacet build of k_connect was level with the generic one at best (7.3 vs 7.1 ms unspilled); only the
+  // walk uses that trait.
   switch (TRACE ? 0 : (lambert && ctx->connect_minb == 6 ? 4 : ctx->connect_minb)) {
     case 4:
       if (lambert) k_connect<TRACE, 4, BDPT_TRAIT_LAMBERT><<<cgrid, threads, 0, ctx->stream>>>(J);
@@ -496,6 +502,10 @@ int bdpt_upload_scene(BdptContext* ctx, const BdptCamera* camera, const BdptMate
   for (uint32_t i = 0; i < n_prims; i++) if (prims[i].type != BDPT_PRIM_TRIANGLE) { traits &= ~BDPT_TRAIT_TRIS; break; }
   for (uint32_t i = 0; i < n_materials; i++)
     if (materials[i].type != BDPT_MAT_DIFFUSE && materials[i].type != BDPT_MAT_EMISSION) { traits &= ~BDPT_TRAIT_LAMBERT; break; }
+  if (!(traits & BDPT_TRAIT_LAMBERT)) {
+    traits |= BDPT_TRAIT_NOMF;
+    for (uint32_t i = 0; i < n_materials; i++) if (materials[i].type == BDPT_MAT_MICROFACET) { traits &= ~BDPT_TRAIT_NOMF; break; }
+  }
   ctx->traits = traits;
   ctx->point_lights = 0;
   for (uint32_t i = 0; i < n_lights; i++) if (lights[i].type == BDPT_LIGHT_POINT) ctx->point_lights = 1;

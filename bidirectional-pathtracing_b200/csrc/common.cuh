@@ -94,6 +94,7 @@ struct alignas(16) Node8 {  // 80 bytes, see bvh8.h
 // half the size.  A trait is a promise about the scene's contents, never a change of behaviour.
 #define BDPT_TRAIT_TRIS 1      // every primitive is a triangle
 #define BDPT_TRAIT_LAMBERT 2   // every material is DiffuseBSDF or EmissionBSDF
+#define BDPT_TRAIT_NOMF 4      // no MicrofacetBSDF (implied by LAMBERT; used when LAMBERT does not hold)
 
 struct DScene {
   const uint4* nodes;       // Node8 as 5 x uint4

@@ -34,6 +34,9 @@ __device__ inline Mat load_mat(const DScene& sc, int m) {
   if (TR & BDPT_TRAIT_LAMBERT) {   // lets the compiler drop every other BSDF from the caller
     if (r.type != BDPT_MAT_EMISSION) r.type = BDPT_MAT_DIFFUSE;
     __builtin_assume(r.type == BDPT_MAT_DIFFUSE || r.type == BDPT_MAT_EMISSION);
+  } else if (TR & BDPT_TRAIT_NOMF) {
+    if (r.type == BDPT_MAT_MICROFACET) r.type = BDPT_MAT_DIFFUSE;
+    __builtin_assume(r.type != BDPT_MAT_MICROFACET);
   }
   r.transmittance = mk3(b.x, b.y, b.z); r.ior = b.w;
   r.radiance = mk3(c.x, c.y, c.z); r.alpha = c.w;

@@ -27,7 +27,7 @@ def run(env):
     return img
 
 base = run({})
-variants = [{"BDPT_SPEC": 0}, {"BDPT_SCHED": 0}, {"BDPT_BATCH_LOG2": 22, "BDPT_BATCH_GIB": 12}]
+variants = [{"BDPT_SPEC": 0}, {"BDPT_SPEC": 5}]
 for v in variants:
     img = run(v)
     d = np.abs(img - base)

@@ -214,6 +214,7 @@ def test_render_matches_oracle_same_random_numbers(api, O, name, m, roulette):
     ("CBspheres_lambertian", {"BDPT_SCHED": "1"}),         # persistent, Lambertian trait only
     ("CBbunny", {"BDPT_SPEC": "0"}),                       # triangle + Lambertian scene on the untraited build
     ("CBgems", {"BDPT_SPEC": "0"}),                        # triangle scene with delta materials on the untraited build
+    ("CBspheres", {"BDPT_SCHED": "1", "BDPT_SPEC": "7"}),  # persistent walk, no-microfacet trait with spheres
     ("CBbunny", {"BDPT_SCHED": "0"}),                      # one subpath per lane on a deep BVH
     ("CBgems", {"BDPT_SCHED": "2"}),                       # per-bounce wavefront walk
 ])
