@@ -46,7 +46,7 @@ struct Builder {
   std::atomic<int> spare_threads{0};
   static constexpr int kMaxBins = 64;
   int kBins = 16;          // SAH bins per axis (BDPT_BVH_BINS, tuning only)
-  static constexpr int kParallelMin = 4096;   // subtrees smaller than this are not worth a thread
+  static constexpr int kParallelMin = 2048;   // subtrees smaller than this are not worth a thread
   int kMaxLeaf = 3;        // primitives per leaf child (<= 3: the node's meta byte counts them in unary)
   float kPrimCost = 0.4f;  // SAH cost of one primitive test relative to one visit of an 8-wide node
 
@@ -62,6 +62,7 @@ struct Builder {
     if (const char* e = getenv("BDPT_BVH_CP")) kPrimCost = (float)atof(e);
     if (const char* e = getenv("BDPT_BVH_BINS")) kBins = std::max(2, std::min(kMaxBins, atoi(e)));
     int hw = (int)std::thread::hardware_concurrency();
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) hw = std::max(1, hw / std::max(1, atoi(e)));   // one process per GPU: share the host
     if (const char* e = getenv("BDPT_BVH_THREADS")) hw = atoi(e);
     spare_threads = std::max(0, std::min(hw, 16) - 1);
   }
@@ -70,6 +71,11 @@ struct Builder {
   // sweeping 3 x 16 bins for every one of the ~2n small nodes was 80 % of the build time.)
   static constexpr int kExactMax = 12;
   int build_small(int me, int first, int count, const Box& cb) {
+    if (count == 2) {   // nothing to choose
+      const int l = build(first, 1), r = build(first + 1, 1);
+      bn[me].left = l; bn[me].right = r;
+      return me;
+    }
     uint32_t ord[kExactMax], best_ord[kExactMax];
     float right_area[kExactMax];
     float best_cost = FLT_MAX; int best_split = -1;
@@ -100,16 +106,27 @@ struct Builder {
     return me;
   }
 
-  int build(int first, int count) {
-    BNode n;
-    n.box.reset();
-    Box cb; cb.reset();
+  // Bounds of the primitives and of their centroids over idx[first, first + count)
+  void bounds(int first, int count, Box* box, Box* cb) const {
+    box->reset(); cb->reset();
     for (int i = first; i < first + count; i++) {
       const BuildPrim& p = prims[idx[i]];
-      n.box.grow(p.lo, p.hi);
+      box->grow(p.lo, p.hi);
       const float* c = &cent[3 * idx[i]];
-      cb.grow(c, c);
+      cb->grow(c, c);
     }
+  }
+
+  int build(int first, int count) {
+    Box box, cb;
+    bounds(first, count, &box, &cb);
+    return build(first, count, box, cb);
+  }
+
+  // `box` / `cb`: bounds of the range's primitives / centroids (the parent computes them while it partitions)
+  int build(int first, int count, const Box& box, const Box& cb) {
+    BNode n;
+    n.box = box;
     n.first = first; n.count = count;
     const int me = next_node.fetch_add(1);
     bn[me] = n;
@@ -149,32 +166,42 @@ struct Builder {
       }
     }
     int mid;
+    Box lbox, lcb, rbox, rcb;
+    bool have_bounds = false;
     if (best_axis < 0) {
       mid = first + count / 2;  // identical centroids: split by index
     } else {
-      float k = kk[best_axis];
-      float lo = cb.lo[best_axis];
-      auto it = std::partition(idx.begin() + first, idx.begin() + first + count, [&](uint32_t id) {
-        int b = std::min(kBins - 1, std::max(0, (int)((cent[3 * id + best_axis] - lo) * k)));
-        return b < best_split;
-      });
-      mid = (int)(it - idx.begin());
-      if (mid == first || mid == first + count) mid = first + count / 2;
+      // partition by bin and collect both halves' bounds in the same pass
+      const float k = kk[best_axis], lo = cb.lo[best_axis];
+      lbox.reset(); lcb.reset(); rbox.reset(); rcb.reset();
+      int i = first, j = first + count - 1;
+      while (i <= j) {
+        const uint32_t id = idx[i];
+        const int b = std::min(kBins - 1, std::max(0, (int)((cent[3 * id + best_axis] - lo) * k)));
+        const BuildPrim& p = prims[id];
+        const float* c = &cent[3 * id];
+        if (b < best_split) { lbox.grow(p.lo, p.hi); lcb.grow(c, c); i++; }
+        else { rbox.grow(p.lo, p.hi); rcb.grow(c, c); std::swap(idx[i], idx[j]); j--; }
+      }
+      mid = i;
+      have_bounds = true;
+      if (mid == first || mid == first + count) { mid = first + count / 2; have_bounds = false; }
     }
+    if (!have_bounds) { bounds(first, mid - first, &lbox, &lcb); bounds(mid, first + count - mid, &rbox, &rcb); }
     // the two halves touch disjoint ranges of idx and claim their nodes from the atomic counter: the left one may
     // run on another thread.  The tree does not depend on which thread built what (node numbers do; the collapse
     // below only follows left / right links).
     int l, r;
     const int nl = mid - first, nr = first + count - mid;
     if (std::min(nl, nr) >= kParallelMin && spare_threads.fetch_sub(1) > 0) {
-      std::thread t([&] { l = build(first, nl); });
-      r = build(mid, nr);
+      std::thread t([&] { l = build(first, nl, lbox, lcb); });
+      r = build(mid, nr, rbox, rcb);
       t.join();
       spare_threads.fetch_add(1);
     } else {
       if (std::min(nl, nr) >= kParallelMin) spare_threads.fetch_add(1);   // undo the failed claim
-      l = build(first, nl);
-      r = build(mid, nr);
+      l = build(first, nl, lbox, lcb);
+      r = build(mid, nr, rbox, rcb);
     }
     bn[me].left = l; bn[me].right = r;
     return me;
@@ -251,6 +278,7 @@ void build_bvh8(const std::vector<BuildPrim>& prims, Bvh8* out) {
     }
   } collect{B, split};
 
+  auto T2b = std::chrono::steady_clock::now();
   struct Item { int wide; int bnode; uint32_t depth; };
   std::deque<Item> queue;
   out->nodes.assign(20, 0u);
@@ -370,7 +398,7 @@ void build_bvh8(const std::vector<BuildPrim>& prims, Bvh8* out) {
   if (getenv("BDPT_BVH_TIMING")) {
     auto T3 = std::chrono::steady_clock::now();
     auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-    fprintf(stderr, "bvh8: setup %.1f ms, sah %.1f ms, collapse+quantise %.1f ms\n", ms(T0, T1), ms(T1, T2), ms(T2, T3));
+    fprintf(stderr, "bvh8: setup %.1f ms, sah %.1f ms, collapse dp %.1f ms, emit %.1f ms\n", ms(T0, T1), ms(T1, T2), ms(T2, T2b), ms(T2b, T3));
   }
 }
 
