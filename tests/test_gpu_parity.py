@@ -279,6 +279,40 @@ def test_config1_full_size_properties(api):
     assert 0.2 < full[0].mean() < 0.8
 
 
+@pytest.mark.parametrize("name,W,H,ns,m", [
+    ("CBspheres_lambertian", 1, 1, 16, 5),     # one pixel: one 8x4 tile with 31 padding lanes
+    ("CBspheres", 7, 5, 3, 5),                 # smaller than a tile in both directions
+    ("CBbunny", 37, 23, 2, 5),                 # ragged in both directions, deep BVH
+    ("CBgems", 33, 9, 1, 1),                   # one sample per pixel, direct lighting only
+    ("CBspheres_lambertian", 16, 12, 4, 0),    # max_ray_depth 0 behaves like 1 (SURVEY Q: m=0 == m=1)
+])
+def test_ragged_frames_and_short_paths_match_oracle(api, O, name, W, H, ns, m):
+    R = make_renderer(api, name, W, H, ns_aa=ns, max_ray_depth=m, seed=31)
+    R.render()
+    gs, ge, gl = (R.framebuffer(i).astype(np.float64) for i in range(3))
+    os_, oe, ol, _ = O.Oracle(load_scene(name), W, H).render(ns, m, rng_mode=1, seed=31, threads=4)
+    assert gs.shape == (H, W, 3) and np.isfinite(gs).all()
+    assert np.allclose(gs, ge + gl, rtol=1e-5, atol=1e-6)
+    assert relmse(ge, oe) <= 2e-3 and relmse(gl, ol) <= 2e-3 and relmse(gs, os_) <= 2e-3
+
+
+def test_image_does_not_depend_on_batching(api, monkeypatch):
+    """The same frame rendered in 2^10-sample batches (hundreds of batches, the last one partial) and in one batch."""
+    name, W, H, ns, m = "CBbunny", 61, 47, 5, 5
+    A = make_renderer(api, name, W, H, ns_aa=ns, max_ray_depth=m, seed=8)
+    A.render()
+    one = [A.framebuffer(i) for i in range(3)]
+    assert A.stats()["n_batches"] == 1
+    A.close()
+    monkeypatch.setenv("BDPT_BATCH_LOG2", "10")
+    B = make_renderer(api, name, W, H, ns_aa=ns, max_ray_depth=m, seed=8)
+    B.render()
+    many = [B.framebuffer(i) for i in range(3)]
+    assert B.stats()["n_batches"] > 10
+    for a, b in zip(one, many):
+        assert np.allclose(a, b, rtol=2e-5, atol=1e-6)   # fp32 atomic summation order only
+
+
 def test_config2_full_size_runs_and_tonemaps(api):
     """configs[1]: CBspheres 480x360, 128 spp, m=5 (mirror + glass)."""
     R = make_renderer(api, "CBspheres", 480, 360, ns_aa=128, max_ray_depth=5, seed=2)
