@@ -159,9 +159,10 @@ int ensure_batch_storage(BdptContext* ctx, size_t B, int m, size_t qcap) {
     // ~30 of these regions at once and its speed moved by up to 30 % with where eight separate cudaMallocs happened
     // to land.  (Tiling the planes per warp, so that a warp reads one 24 KB window, measured 13 % slower: the planes
     // being far apart is what spreads a warp's loads over the HBM channels.)
+    const size_t nB = std::max(B, ctx->cap_B); const int nm = std::max(m, ctx->cap_m); const size_t nq = std::max(qcap, ctx->cap_q);
     dfree(ctx->slab);
     ctx->v0 = ctx->v1 = ctx->v2 = ctx->v3 = nullptr; ctx->q0 = ctx->q1 = ctx->q2 = nullptr; ctx->counts = nullptr;
-    const size_t nB = std::max(B, ctx->cap_B); const int nm = std::max(m, ctx->cap_m); const size_t nq = std::max(qcap, ctx->cap_q);
+    ctx->cap_B = 0; ctx->cap_m = -1; ctx->cap_q = 0;   // nothing is held until the allocation below succeeds
     const size_t n = 2 * (size_t)(nm + 1) * nB;
     const size_t align = (size_t)ctx->slab_align_kb << 10;
     auto up = [&](size_t x) { return (x + align - 1) / align * align; };
@@ -573,9 +574,16 @@ int bdpt_render(BdptContext* ctx, const BdptRenderParams* p) {
   const int tiles_x = (ctx->W + 7) / 8, npix_pad = tiles_x * ((ctx->H + 3) / 4) * 32;
   const unsigned long long total = (unsigned long long)npix_pad * (unsigned long long)p->n_samples;
   if (total < B) B = (size_t)((total + 1023) & ~1023ull);
-  const size_t qcap = B * (size_t)(m + 1) * (size_t)(m + 1);
-  rc = ensure_batch_storage(ctx, B, m, std::max<size_t>(qcap, 1024));
-  if (rc) return rc;
+  // If the device cannot give the slab (another context holds the memory), halve the batch until it can: the image
+  // does not depend on the batch size, only the kernels' tails do.
+  for (;;) {
+    const size_t qcap = B * (size_t)(m + 1) * (size_t)(m + 1);
+    rc = ensure_batch_storage(ctx, B, m, std::max<size_t>(qcap, 1024));
+    if (rc == BDPT_OK) break;
+    cudaGetLastError();   // clear the allocation error
+    if (B <= 65536) return rc;
+    B = std::max<size_t>((B / 2) & ~(size_t)1023, 1024);
+  }
   fill_job(ctx, p, &J);
   J.B = (int)B; J.g_end = total;
   // the planes are indexed with the job's own B and m (VSLOT), capacity may be larger
