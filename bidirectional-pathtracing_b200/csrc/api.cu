@@ -269,13 +269,15 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
   const bool lambert = !TRACE && (ctx->spec & 2) && (ctx->traits & BDPT_TRAIT_LAMBERT);
   // The Lambert build needs 96 registers unspilled and runs best that way (5 CTAs/SM); forced to 80 registers it is
   // slower than the generic build at 80, which tolerates its spills (measured: 6.3 / 9.7 / 7.2 ms per 2^24 samples).
-  // A no-microfacet build of k_connect was level with the generic one at best (7.3 vs 7.1 ms unspilled); only the
-  // walk uses that trait.
-  switch (TRACE ? 0 : (lambert && ctx->connect_minb == 6 ? 4 : ctx->connect_minb)) {
+  // The no-microfacet build likewise: 6.3 ms at 96 registers (bounds 5), 7.3 at 103 (bounds 4), 9.7 at 80 (bounds 6);
+  // the generic build 7.1 at 80.
+  const bool nomf = !TRACE && (ctx->spec & 2) && (ctx->traits & BDPT_TRAIT_NOMF);
+  switch (TRACE ? 0 : (ctx->connect_minb != 6 ? ctx->connect_minb : lambert ? 4 : nomf ? 5 : 6)) {
     case 4:
       if (lambert) k_connect<TRACE, 4, BDPT_TRAIT_LAMBERT><<<cgrid, threads, 0, ctx->stream>>>(J);
       else k_connect<TRACE, 4><<<cgrid, threads, 0, ctx->stream>>>(J);
       break;
+    case 5: k_connect<TRACE, 5, BDPT_TRAIT_NOMF><<<cgrid, threads, 0, ctx->stream>>>(J); break;
     case 6:
       if (lambert) k_connect<TRACE, 6, BDPT_TRAIT_LAMBERT><<<cgrid, threads, 0, ctx->stream>>>(J);
       else k_connect<TRACE, 6><<<cgrid, threads, 0, ctx->stream>>>(J);
