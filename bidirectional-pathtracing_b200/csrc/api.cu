@@ -245,12 +245,12 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
     const size_t shm = (size_t)J.ntop * 80;
     if (ctx->variant == 1) k_walk_pt<16, 8, 4><<<g, threads, shm, ctx->stream>>>(J);
     else switch ((ctx->spec & 1) ? ctx->traits : 0) {
-      case 1: k_walk_pt<16, 8, 6, 1><<<g, threads, shm, ctx->stream>>>(J); break;
-      case 2: k_walk_pt<16, 8, 6, 2><<<g, threads, shm, ctx->stream>>>(J); break;
-      case 3: k_walk_pt<16, 8, 6, 3><<<g, threads, shm, ctx->stream>>>(J); break;
-      case 4: k_walk_pt<16, 8, 6, 4><<<g, threads, shm, ctx->stream>>>(J); break;
-      case 5: k_walk_pt<16, 8, 6, 5><<<g, threads, shm, ctx->stream>>>(J); break;
-      default: k_walk_pt<16, 8, 6, 0><<<g, threads, shm, ctx->stream>>>(J); break;
+      case 1: k_walk_pt<14, 6, 6, 1><<<g, threads, shm, ctx->stream>>>(J); break;
+      case 2: k_walk_pt<14, 6, 6, 2><<<g, threads, shm, ctx->stream>>>(J); break;
+      case 3: k_walk_pt<14, 6, 6, 3><<<g, threads, shm, ctx->stream>>>(J); break;
+      case 4: k_walk_pt<14, 6, 6, 4><<<g, threads, shm, ctx->stream>>>(J); break;
+      case 5: k_walk_pt<14, 6, 6, 5><<<g, threads, shm, ctx->stream>>>(J); break;
+      default: k_walk_pt<14, 6, 6, 0><<<g, threads, shm, ctx->stream>>>(J); break;
     }
   }
   else {
