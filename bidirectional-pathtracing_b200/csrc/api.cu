@@ -170,7 +170,9 @@ int ensure_batch_storage(BdptContext* ctx, size_t B, int m, size_t qcap) {
     const size_t total = 4 * sz_v + 3 * sz_q + sz_c + align;
     CK(cudaMalloc(&ctx->slab, total));
     char* base = (char*)(((uintptr_t)ctx->slab + align - 1) / align * align);
-    ctx->v0 = (float4*)base; ctx->v1 = (float4*)(base + sz_v); ctx->v2 = (float4*)(base + 2 * sz_v); ctx->v3 = (float4*)(base + 3 * sz_v);
+    // one 64-byte record per vertex (v0..v3 are its four float4): a lane's four stores in the walk fill two whole
+    // 32-byte sectors (as four separate planes they were partial-sector writes and DRAM saw 2x the bytes)
+    ctx->v0 = (float4*)base; ctx->v1 = ctx->v0 + 1; ctx->v2 = ctx->v0 + 2; ctx->v3 = ctx->v0 + 3;
     ctx->q0 = (float4*)(base + 4 * sz_v); ctx->q1 = (float4*)(base + 4 * sz_v + sz_q); ctx->q2 = (float4*)(base + 4 * sz_v + 2 * sz_q);
     ctx->counts = (int*)(base + 4 * sz_v + 3 * sz_q);
     ctx->cap_B = nB; ctx->cap_m = nm; ctx->cap_q = nq;
@@ -791,11 +793,11 @@ int bdpt_trace_sample(BdptContext* ctx, const BdptRenderParams* p, int x, int y,
   J.acc_eye = se; J.acc_light = sl; J.dbg = dbg;
   J.B = (int)B; J.g0 = 0; J.g_end = 1; J.single_x = x; J.single_y = y;
   rc = run_batch<true>(ctx, J, -1);
-  std::vector<float4> hv[4]; std::vector<int> hc(2 * B);
+  std::vector<float4> hv; std::vector<int> hc(2 * B);
   size_t nv = 2 * (size_t)(m + 1) * B;
   if (rc == BDPT_OK) {
-    float4* planes[4] = {ctx->v0, ctx->v1, ctx->v2, ctx->v3};
-    for (int k = 0; k < 4; k++) { hv[k].resize(nv); cudaMemcpyAsync(hv[k].data(), planes[k], nv * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream); }
+    hv.resize(4 * nv);   // 64-byte records: four float4 per vertex
+    cudaMemcpyAsync(hv.data(), ctx->v0, 4 * nv * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream);
     cudaMemcpyAsync(hc.data(), ctx->counts, 2 * B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
     cudaMemcpyAsync(hdbg.data(), dbg, ndbg * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
   }
@@ -819,7 +821,7 @@ int bdpt_trace_sample(BdptContext* ctx, const BdptRenderParams* p, int x, int y,
         r[6] = r[7] = r[8] = 1.0; r[9] = 1.0; r[10] = -1; r[12] = 1.0;
       } else {
         size_t s = (size_t)(kind * (m + 1) + (j - 1)) * B;
-        float4 a = hv[0][s], b = hv[1][s], c = hv[2][s], d = hv[3][s];
+        float4 a = hv[4 * s], b = hv[4 * s + 1], c = hv[4 * s + 2], d = hv[4 * s + 3];
         int mat; memcpy(&mat, &a.w, 4);
         r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = b.x; r[4] = b.y; r[5] = b.z;
         r[6] = c.x; r[7] = c.y; r[8] = c.z; r[10] = mat;

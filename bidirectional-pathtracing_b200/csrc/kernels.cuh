@@ -33,7 +33,7 @@ namespace bdpt {
 struct Job {
   DScene sc;
   DCamera cam;
-  // vertex planes, each [2*(m+1)][B] float4; counts [2][B]
+  // vertex records [2*(m+1)][B] x 64 bytes (v0..v3: the four float4 of a record, interleaved); counts [2][B]
   float4 *v0, *v1, *v2, *v3;
   int* counts;
   // shadow queue, SoA float4 x 3, and its counters {n_entries, cursor, overflow, -}
@@ -76,7 +76,8 @@ __device__ inline bool decode_sample(const Job& J, unsigned long long g, int* x,
   return *x < J.cam.W && *y < J.cam.H;
 }
 
-#define VSLOT(J, kind, j, i) ((size_t)((kind) * ((J).m + 1) + ((j)-1)) * (size_t)(J).B + (size_t)(i))
+// float4 index of the first quarter of the 64-byte record of vertex j of subpath (kind, i); v1..v3 = v0 + 1..3
+#define VSLOT(J, kind, j, i) (4 * ((size_t)((kind) * ((J).m + 1) + ((j)-1)) * (size_t)(J).B + (size_t)(i)))
 
 __device__ inline float clampS(float s) { return fminf(s, 1e30f); }
 
