@@ -79,6 +79,21 @@ __device__ inline bool decode_sample(const Job& J, unsigned long long g, int* x,
 // float4 index of the first quarter of the 64-byte record of vertex j of subpath (kind, i); v1..v3 = v0 + 1..3
 #define VSLOT(J, kind, j, i) (4 * ((size_t)((kind) * ((J).m + 1) + ((j)-1)) * (size_t)(J).B + (size_t)(i)))
 
+// 32-byte global accesses (LDG.256 / STG.256, sm_100): half of a vertex record per instruction
+__device__ inline void ld256(const float4* p, float4* a, float4* b) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a->x), "=f"(a->y), "=f"(a->z), "=f"(a->w), "=f"(b->x), "=f"(b->y), "=f"(b->z), "=f"(b->w) : "l"(p));
+}
+__device__ inline void st256(float4* p, float4 a, float4 b) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
+// the 64-byte record of a vertex: {pos, material | n, D | alpha, S | wo, q}
+__device__ inline void store_vertex(const Job& J, size_t slot, float4 a, float4 b, float4 c, float4 e) {
+  st256(J.v0 + slot, a, b);
+  st256(J.v0 + slot + 2, c, e);
+}
+
 __device__ inline float clampS(float s) { return fminf(s, 1e30f); }
 
 // ---------------------------------------------------------------------------------------- walk
@@ -117,10 +132,10 @@ __global__ void __launch_bounds__(128) k_walk(const Job J) {
     prev_n = nl; alpha = Le * (1.0f / pA); prev_pdf = pdir;
     pdfeval_prev = pdir; D_prev = pA; S_prev = 1.f;
     size_t s1 = VSLOT(J, 1, 1, si);
-    J.v0[s1] = make_float4(o.x, o.y, o.z, __int_as_float(-1));
-    J.v1[s1] = make_float4(nl.x, nl.y, nl.z, pA);
-    J.v2[s1] = make_float4(alpha.x, alpha.y, alpha.z, 1.f);
-    J.v3[s1] = make_float4(pdir, 0.f, 0.f, 1.f);
+    store_vertex(J, s1, make_float4(o.x, o.y, o.z, __int_as_float(-1)),
+                 make_float4(nl.x, nl.y, nl.z, pA),
+                 make_float4(alpha.x, alpha.y, alpha.z, 1.f),
+                 make_float4(pdir, 0.f, 0.f, 1.f));
   }
 
   unsigned int nrays = 0;
@@ -156,10 +171,10 @@ __global__ void __launch_bounds__(128) k_walk(const Job J) {
     S_j = clampS(S_j);
 
     size_t sl = VSLOT(J, kind, j, si);
-    J.v0[sl] = make_float4(hit_p.x, hit_p.y, hit_p.z, __int_as_float(mat));
-    J.v1[sl] = make_float4(n.x, n.y, n.z, D_j);
-    J.v2[sl] = make_float4(alpha.x, alpha.y, alpha.z, S_j);
-    J.v3[sl] = make_float4(-d.x, -d.y, -d.z, p_keep);
+    store_vertex(J, sl, make_float4(hit_p.x, hit_p.y, hit_p.z, __int_as_float(mat)),
+                 make_float4(n.x, n.y, n.z, D_j),
+                 make_float4(alpha.x, alpha.y, alpha.z, S_j),
+                 make_float4(-d.x, -d.y, -d.z, p_keep));
     nv = j;
     if (j >= J.m + 1) break;
     if (J.roulette && !(rng.uniform() < p_keep)) break;
@@ -185,7 +200,8 @@ struct Vtx {
 
 __device__ inline Vtx load_vtx(const Job& J, int kind, int j, int si) {
   size_t s = VSLOT(J, kind, j, si);
-  float4 a = J.v0[s], b = J.v1[s], c = J.v2[s], e = J.v3[s];
+  float4 a, b, c, e;
+  ld256(J.v0 + s, &a, &b); ld256(J.v0 + s + 2, &c, &e);
   Vtx v;
   v.pos = mk3(a.x, a.y, a.z); v.mat = __float_as_int(a.w);
   v.n = mk3(b.x, b.y, b.z); v.D = b.w;
@@ -214,7 +230,7 @@ __device__ inline void push_shadow(const Job& J, bool push, f3 o, f3 dir, float 
 struct VRaw { float4 a, b, c, e; };
 __device__ inline VRaw load_raw(const Job& J, int kind, int j, int si) {
   size_t s = VSLOT(J, kind, j, si);
-  VRaw r; r.a = J.v0[s]; r.b = J.v1[s]; r.c = J.v2[s]; r.e = J.v3[s];
+  VRaw r; ld256(J.v0 + s, &r.a, &r.b); ld256(J.v0 + s + 2, &r.c, &r.e);
   return r;
 }
 __device__ inline Vtx unpack(const VRaw& r) {
@@ -232,7 +248,7 @@ __device__ inline Vtx unpack(const VRaw& r) {
 struct GlobalVerts {
   const Job& J; int si;
   __device__ inline Vtx get(int kind, int j) const { return load_vtx(J, kind, j, si); }
-  __device__ inline void light_origin(float4* a, float4* b) const { size_t s1 = VSLOT(J, 1, 1, si); *a = J.v0[s1]; *b = J.v1[s1]; }
+  __device__ inline void light_origin(float4* a, float4* b) const { size_t s1 = VSLOT(J, 1, 1, si); ld256(J.v0 + s1, a, b); }
 };
 // All strategies (s = 0 .. nL) of one (sample, t): estimate_bidirection_radiance + the closed-form MIS weight.
 template <bool TRACE, int TR, class VERTS>
@@ -603,10 +619,10 @@ __device__ inline bool walk_begin(const Job& J, unsigned i, WalkState& W, Trav& 
     W.prev_n = nl; W.alpha = Le * (1.0f / pA); W.prev_pdf = pdir;
     W.pdfeval_prev = pdir; W.D_prev = pA; W.S_prev = 1.f;
     size_t s1 = VSLOT(J, 1, 1, W.si);
-    J.v0[s1] = make_float4(o.x, o.y, o.z, __int_as_float(-1));
-    J.v1[s1] = make_float4(nl.x, nl.y, nl.z, pA);
-    J.v2[s1] = make_float4(W.alpha.x, W.alpha.y, W.alpha.z, 1.f);
-    J.v3[s1] = make_float4(pdir, 0.f, 0.f, 1.f);
+    store_vertex(J, s1, make_float4(o.x, o.y, o.z, __int_as_float(-1)),
+                 make_float4(nl.x, nl.y, nl.z, pA),
+                 make_float4(W.alpha.x, W.alpha.y, W.alpha.z, 1.f),
+                 make_float4(pdir, 0.f, 0.f, 1.f));
     T.begin(o, d, BDPT_EPS_F, INFINITY);
   }
   return true;
@@ -646,10 +662,10 @@ __device__ inline bool walk_shade(const Job& J, WalkState& W, Trav& T) {
   S_j = clampS(S_j);
 
   size_t sl = VSLOT(J, W.kind, W.j, W.si);
-  J.v0[sl] = make_float4(hit_p.x, hit_p.y, hit_p.z, __int_as_float(mat));
-  J.v1[sl] = make_float4(n.x, n.y, n.z, D_j);
-  J.v2[sl] = make_float4(W.alpha.x, W.alpha.y, W.alpha.z, S_j);
-  J.v3[sl] = make_float4(-d.x, -d.y, -d.z, p_keep);
+  store_vertex(J, sl, make_float4(hit_p.x, hit_p.y, hit_p.z, __int_as_float(mat)),
+               make_float4(n.x, n.y, n.z, D_j),
+               make_float4(W.alpha.x, W.alpha.y, W.alpha.z, S_j),
+               make_float4(-d.x, -d.y, -d.z, p_keep));
   W.nv = W.j;
   if (W.j >= J.m + 1) return false;
   if (J.roulette && !(W.rng.uniform() < p_keep)) return false;
