@@ -173,7 +173,8 @@ int ensure_batch_storage(BdptContext* ctx, size_t B, int m, size_t qcap) {
     // one 64-byte record per vertex (v0..v3 are its four float4): a lane's four stores in the walk fill two whole
     // 32-byte sectors (as four separate planes they were partial-sector writes and DRAM saw 2x the bytes)
     ctx->v0 = (float4*)base; ctx->v1 = ctx->v0 + 1; ctx->v2 = ctx->v0 + 2; ctx->v3 = ctx->v0 + 3;
-    ctx->q0 = (float4*)(base + 4 * sz_v); ctx->q1 = (float4*)(base + 4 * sz_v + sz_q); ctx->q2 = (float4*)(base + 4 * sz_v + 2 * sz_q);
+    // shadow queue: 32-byte ray records {q0, q1} interleaved (q1 = q0 + 1, stride 2), contributions q2 as a plane
+    ctx->q0 = (float4*)(base + 4 * sz_v); ctx->q1 = ctx->q0 + 1; ctx->q2 = (float4*)(base + 4 * sz_v + 2 * sz_q);
     ctx->counts = (int*)(base + 4 * sz_v + 3 * sz_q);
     ctx->cap_B = nB; ctx->cap_m = nm; ctx->cap_q = nq;
   }

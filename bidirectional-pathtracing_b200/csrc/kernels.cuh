@@ -222,8 +222,8 @@ __device__ inline void push_shadow(const Job& J, bool push, f3 o, f3 dir, float 
   if (!push) return;
   unsigned int idx = base + __popc(mask & ((1u << lane) - 1u));
   if (idx >= J.qcap) { J.qctr[2] = 1u; return; }
-  J.q0[idx] = make_float4(o.x, o.y, o.z, tmax);
-  J.q1[idx] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(target));
+  // the ray {o, tmax | dir, pixel} is one 32-byte record (q0 / q1 interleaved), its contribution a separate plane
+  st256(J.q0 + 2 * (size_t)idx, make_float4(o.x, o.y, o.z, tmax), make_float4(dir.x, dir.y, dir.z, __uint_as_float(target)));
   J.q2[idx] = make_float4(ill.x, ill.y, ill.z, 0.f);
 }
 
@@ -453,8 +453,8 @@ __global__ void __launch_bounds__(128, MINB) k_connect(const Job J) {
 // 60 ms.  There, lanes of the set that splat the same light-image pixel are summed first and their leader issues the
 // three atomics.
 __device__ inline void shadow_splat(const Job& J, unsigned mask, unsigned idx) {
-  float4 b = J.q1[idx], c = J.q2[idx];
-  const unsigned int tg = __float_as_uint(b.w);
+  const float4 c = J.q2[idx];
+  const unsigned int tg = __float_as_uint(J.q1[2 * (size_t)idx].w);
   float sx = c.x, sy = c.y, sz = c.z;
   if (J.point_lights) {
     const unsigned li = __ballot_sync(mask, (tg & 0x80000000u) != 0u);
@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(128) k_shadow(const Job J) {
     if (base >= n) break;
     unsigned int idx = base + lane;
     if (idx < n) {
-      float4 a = J.q0[idx], b = J.q1[idx];
+      float4 a, b; ld256(J.q0 + 2 * (size_t)idx, &a, &b);
       Hit h = traverse<true, TR>(J.sc, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), BDPT_EPS_F, a.w);
       traced++;
       const unsigned clear = __ballot_sync(__activemask(), h.leaf < 0);
@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(128, MINB) k_shadow_pt(const Job J) {
     if (!wf.exhausted && (__popc(idle) >= FETCH || idle == 0xffffffffu)) {
       unsigned my = warp_fetch(J.qctr + 1, n, 256u, !active, wf);
       if (my != BDPT_NONE) {
-        float4 a = J.q0[my], b = J.q1[my];
+        float4 a, b; ld256(J.q0 + 2 * (size_t)my, &a, &b);
         T.begin(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), BDPT_EPS_F, a.w);
         idx = my; active = true;
       }
