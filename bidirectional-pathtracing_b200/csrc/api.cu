@@ -48,9 +48,11 @@ struct BdptContext {
   // batch storage
   size_t cap_B = 0; int cap_m = -1; size_t cap_q = 0;
   char* slab = nullptr;        // backing store of v0..v3, q0..q2, counts
+  size_t slab_bytes = 0, slab_sz_v = 0, slab_sz_q = 0;
   int slab_align_kb = 2048;    // BDPT_SLAB_ALIGN_KB, tuning only
   float4 *v0 = nullptr, *v1 = nullptr, *v2 = nullptr, *v3 = nullptr, *q0 = nullptr, *q1 = nullptr, *q2 = nullptr;
   int* counts = nullptr;
+  char* counters = nullptr;    // 2 MiB block holding qctr and d_stats
   unsigned int* qctr = nullptr;
   unsigned long long* d_stats = nullptr;
   unsigned int* h_qctr = nullptr;  // pinned
@@ -153,12 +155,24 @@ void make_build_prims(const BdptPrim* prims, uint32_t n_prims, std::vector<Build
   }
 }
 
+// Points the context's vertex / queue / count arrays into a slab.
+void carve_slab(BdptContext* ctx, char* slab) {
+  const size_t align = (size_t)ctx->slab_align_kb << 10;
+  char* base = (char*)(((uintptr_t)slab + align - 1) / align * align);
+  const size_t sz_v = ctx->slab_sz_v, sz_q = ctx->slab_sz_q;
+  // one 64-byte record per vertex (v0..v3 are its four float4): a lane's four stores in the walk fill two whole
+  // 32-byte sectors (as four separate planes they were partial-sector writes and DRAM saw 2x the bytes)
+  ctx->v0 = (float4*)base; ctx->v1 = ctx->v0 + 1; ctx->v2 = ctx->v0 + 2; ctx->v3 = ctx->v0 + 3;
+  // shadow queue: 32-byte ray records {q0, q1} interleaved (q1 = q0 + 1, stride 2), contributions q2 as a plane
+  ctx->q0 = (float4*)(base + 4 * sz_v); ctx->q1 = ctx->q0 + 1; ctx->q2 = (float4*)(base + 4 * sz_v + 2 * sz_q);
+  ctx->counts = (int*)(base + 4 * sz_v + 3 * sz_q);
+}
+
 int ensure_batch_storage(BdptContext* ctx, size_t B, int m, size_t qcap) {
   if (B > ctx->cap_B || m > ctx->cap_m || qcap > ctx->cap_q) {
-    // One slab for the vertex planes, the counts and the shadow queue, carved at 2 MiB boundaries: k_connect reads
-    // ~30 of these regions at once and its speed moved by up to 30 % with where eight separate cudaMallocs happened
-    // to land.  (Tiling the planes per warp, so that a warp reads one 24 KB window, measured 13 % slower: the planes
-    // being far apart is what spreads a warp's loads over the HBM channels.)
+    // One slab for the vertex records, the counts and the shadow queue, carved at 2 MiB boundaries.  (Tiling the
+    // records per warp, so that a warp reads one 24 KB window, measured 13 % slower: the path positions being far
+    // apart is what spreads a warp's loads over the HBM channels.)
     const size_t nB = std::max(B, ctx->cap_B); const int nm = std::max(m, ctx->cap_m); const size_t nq = std::max(qcap, ctx->cap_q);
     dfree(ctx->slab);
     ctx->v0 = ctx->v1 = ctx->v2 = ctx->v3 = nullptr; ctx->q0 = ctx->q1 = ctx->q2 = nullptr; ctx->counts = nullptr;
@@ -169,13 +183,8 @@ int ensure_batch_storage(BdptContext* ctx, size_t B, int m, size_t qcap) {
     const size_t sz_v = up(n * sizeof(float4)), sz_q = up(nq * sizeof(float4)), sz_c = up(2 * nB * sizeof(int));
     const size_t total = 4 * sz_v + 3 * sz_q + sz_c + align;
     CK(cudaMalloc(&ctx->slab, total));
-    char* base = (char*)(((uintptr_t)ctx->slab + align - 1) / align * align);
-    // one 64-byte record per vertex (v0..v3 are its four float4): a lane's four stores in the walk fill two whole
-    // 32-byte sectors (as four separate planes they were partial-sector writes and DRAM saw 2x the bytes)
-    ctx->v0 = (float4*)base; ctx->v1 = ctx->v0 + 1; ctx->v2 = ctx->v0 + 2; ctx->v3 = ctx->v0 + 3;
-    // shadow queue: 32-byte ray records {q0, q1} interleaved (q1 = q0 + 1, stride 2), contributions q2 as a plane
-    ctx->q0 = (float4*)(base + 4 * sz_v); ctx->q1 = ctx->q0 + 1; ctx->q2 = (float4*)(base + 4 * sz_v + 2 * sz_q);
-    ctx->counts = (int*)(base + 4 * sz_v + 3 * sz_q);
+    ctx->slab_bytes = total; ctx->slab_sz_v = sz_v; ctx->slab_sz_q = sz_q;
+    carve_slab(ctx, ctx->slab);
     ctx->cap_B = nB; ctx->cap_m = nm; ctx->cap_q = nq;
   }
   if (ctx->sched == 2 && (2 * B > ctx->wf_cap || m > ctx->wf_cap_m)) {
@@ -191,8 +200,14 @@ int ensure_batch_storage(BdptContext* ctx, size_t B, int m, size_t qcap) {
     ctx->wf_cap = n; ctx->wf_cap_m = nm;
   }
   if (!ctx->qctr) {
-    CK(cudaMalloc(&ctx->qctr, 4 * sizeof(unsigned int)));
-    CK(cudaMalloc(&ctx->d_stats, 4 * sizeof(unsigned long long)));
+    // The queue counter is the hottest address of k_connect (one returning atomic per warp and strategy, ~12 M per
+    // batch).  As a 16-byte cudaMalloc it shared a small-allocation page with the materials, the lights and the
+    // statistics, all read or updated by the same kernel, and k_connect took 5.9 to 8.2 ms per 2^24 samples depending
+    // on how those happened to sit together (different per context, stable within one).  In a block of its own,
+    // statistics a megabyte away, it is 5.9 ms every time.
+    CK(cudaMalloc(&ctx->counters, (size_t)2 << 20));
+    ctx->qctr = (unsigned int*)ctx->counters;
+    ctx->d_stats = (unsigned long long*)(ctx->counters + ((size_t)1 << 20));
     CK(cudaMemset(ctx->d_stats, 0, 4 * sizeof(unsigned long long)));
     CK(cudaMallocHost(&ctx->h_qctr, 4 * sizeof(unsigned int)));
   }
@@ -382,7 +397,7 @@ void bdpt_destroy(BdptContext* ctx) {
   cudaStreamSynchronize(ctx->stream);
   dfree(ctx->d_nodes); dfree(ctx->d_prims); dfree(ctx->d_shading); dfree(ctx->d_mats); dfree(ctx->d_lights); dfree(ctx->d_prims64);
   dfree(ctx->acc_eye); dfree(ctx->acc_light); dfree(ctx->resolve_tmp); dfree(ctx->rgba_tmp);
-  dfree(ctx->slab); dfree(ctx->qctr); dfree(ctx->d_stats);
+  dfree(ctx->slab); dfree(ctx->counters); ctx->qctr = nullptr; ctx->d_stats = nullptr;
   { WfBuf& F = ctx->wf; dfree(F.r0); dfree(F.r1); dfree(F.h); dfree(F.s0); dfree(F.s1); dfree(F.s2); dfree(F.s3); dfree(F.s4); dfree(F.queue_a); dfree(F.queue_b); dfree(F.ctr); }
   if (ctx->h_qctr) cudaFreeHost(ctx->h_qctr);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
