@@ -229,6 +229,7 @@ void fill_job(BdptContext* ctx, const BdptRenderParams* p, Job* J) {
   J->seed = p->seed; J->m = std::max(1, p->max_ray_depth); J->first_sample = p->first_sample;
   J->tiles_x = (ctx->W + 7) / 8;
   J->npix_pad = J->tiles_x * ((ctx->H + 3) / 4) * 32;
+  J->div_tiles_x = make_fastdiv((uint32_t)J->tiles_x); J->div_npix_pad = make_fastdiv((uint32_t)J->npix_pad);
   J->roulette = (p->flags & BDPT_FLAG_ROULETTE) ? 1 : 0;
   J->no_mis = (p->flags & BDPT_FLAG_NO_MIS) ? 1 : 0;
   J->ntop = std::min(ctx->top_nodes, ctx->sc.n_nodes);

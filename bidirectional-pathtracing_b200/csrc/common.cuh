@@ -112,6 +112,28 @@ struct DScene {
   uint32_t qbias_bits;
 };
 
+// Division of a 32-bit unsigned by a divisor fixed for the whole launch (Granlund & Montgomery 1994, the branch-free
+// form): q = (t + ((n - t) >> s1)) >> s2 with t = umulhi(m, n); exact for every n < 2^32.  The hardware has no integer
+// divide, so `n / d` is ~25 instructions; this is 4.
+struct FastDiv {
+  uint32_t d, m, s1, s2;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f; f.d = d;
+  uint32_t L = 0; while (L < 32 && ((uint64_t)1 << L) < d) L++;
+  f.m = (uint32_t)((((uint64_t)1 << 32) * (((uint64_t)1 << L) - d)) / d + 1);
+  f.s1 = L < 1 ? L : 1; f.s2 = L > 1 ? L - 1 : 0;
+  return f;
+}
+__host__ __device__ inline uint32_t fast_div(uint32_t n, const FastDiv& f) {
+#ifdef __CUDA_ARCH__
+  const uint32_t t = __umulhi(f.m, n);
+#else
+  const uint32_t t = (uint32_t)(((uint64_t)f.m * n) >> 32);
+#endif
+  return (t + ((n - t) >> f.s1)) >> f.s2;
+}
+
 // 1/x by the SFU alone (MUFU.RCP, <= 1 ulp on normal inputs; denormals flush): __fdividef(1, x) adds a range fix-up
 __device__ inline float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 

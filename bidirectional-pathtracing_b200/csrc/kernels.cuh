@@ -52,6 +52,7 @@ struct Job {
   int m;                      // max_ray_depth
   int first_sample;           // sample index of job-sample 0
   int tiles_x, npix_pad;      // 8x4 pixel tiles per row; padded pixel count
+  FastDiv div_tiles_x, div_npix_pad;
   int roulette;
   int ntop;                   // BVH nodes staged in shared memory by the persistent kernels
   int no_mis;                 // weight 1 for every strategy: the reference's own debug switch (bidirection.cpp:124-126)
@@ -66,10 +67,11 @@ __device__ inline bool decode_sample(const Job& J, unsigned long long g, int* x,
   if (g >= J.g_end) return false;
   if (J.single_x >= 0) { *x = J.single_x; *y = J.single_y; *sample = J.first_sample + (int)g; return true; }
   unsigned int q = J.p0 + (unsigned int)(g - J.g0);   // < npix_pad + B < 2^32
-  unsigned int k = J.k0 + q / (unsigned int)J.npix_pad;
-  int p = (int)(q % (unsigned int)J.npix_pad);
+  const unsigned int qd = fast_div(q, J.div_npix_pad);
+  unsigned int k = J.k0 + qd;
+  int p = (int)(q - qd * (unsigned int)J.npix_pad);
   int tile = p >> 5, w = p & 31;
-  int tx = tile % J.tiles_x, ty = tile / J.tiles_x;
+  const int ty = (int)fast_div((unsigned int)tile, J.div_tiles_x), tx = tile - ty * J.tiles_x;
   *x = tx * 8 + (w & 7);
   *y = ty * 4 + (w >> 3);
   *sample = J.first_sample + (int)k;
