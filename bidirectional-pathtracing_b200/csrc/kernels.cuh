@@ -365,7 +365,17 @@ __device__ inline void connect_strategies(const Job& J, const int si, const int 
       contrib = eye_alpha * Lv.alpha * (f_eye * f_light) * g;
       bool push = false;
       unsigned int target = pix_own;
-      if (norm(contrib) > BDPT_EPS_F) {
+      const bool gate = norm(contrib) > BDPT_EPS_F;
+      // The queue slot is reserved here, before the weight is known: the atomic's round trip to L2 (ncu put 23 % of
+      // this kernel's stall samples on it) then overlaps the weight computation.  A connection that passes the gate
+      // but ends up not pushed (weight 0 / NaN, or off-frame for t = 1: rare) fills its slot with a null ray.
+      unsigned int r_active = 0u, r_mask = 0u, r_ticket = 0u;
+      if (!TRACE) {
+        r_active = __activemask();
+        r_mask = __ballot_sync(r_active, gate);
+        if (r_mask != 0u && (int)(threadIdx.x & 31) == __ffs(r_mask) - 1) r_ticket = atomicAdd(J.qctr + 0, (unsigned int)__popc(r_mask));
+      }
+      if (gate) {
         // ---- MIS weight (bidirection.cpp:121-293 in closed form, see header)
         double winv = 1.0;
         if (t >= 2) {
@@ -423,7 +433,23 @@ __device__ inline void connect_strategies(const Job& J, const int si, const int 
         Hit h = traverse<true, TR>(sc, ve_pos, cdir, BDPT_EPS_F, dist - BDPT_EPS_F);
         if (h.leaf >= 0) { contrib = mk3(NAN); w = NAN; push = false; eye_x = eye_y = -1; }
       }
-      push_shadow(J, push, ve_pos, cdir, dist - BDPT_EPS_F, target, ill);
+      if (TRACE) {
+        push_shadow(J, push, ve_pos, cdir, dist - BDPT_EPS_F, target, ill);
+      } else if (r_mask != 0u) {
+        const unsigned int lane = threadIdx.x & 31;
+        const unsigned int base = __shfl_sync(r_active, r_ticket, __ffs(r_mask) - 1);
+        if (gate) {
+          const unsigned int idx = base + __popc(r_mask & ((1u << lane) - 1u));
+          if (idx >= J.qcap) J.qctr[2] = 1u;
+          else {
+            const float tmax = push ? dist - BDPT_EPS_F : -1.f;     // null ray: nothing to hit, adds zero
+            const f3 add = push ? ill : zero;
+            st256(J.q0 + 2 * (size_t)idx, make_float4(ve_pos.x, ve_pos.y, ve_pos.z, tmax),
+                  make_float4(cdir.x, cdir.y, cdir.z, __uint_as_float(push ? target : pix_own)));
+            J.q2[idx] = make_float4(add.x, add.y, add.z, 0.f);
+          }
+        }
+      }
     }
     if (TRACE && J.dbg) {
       double* r = J.dbg + 8 * ((size_t)(t - 1) * (size_t)(J.m + 2) + (size_t)s);
