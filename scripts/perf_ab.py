@@ -11,7 +11,7 @@ W, H, spp, m = (int(a) for a in sys.argv[2:6]) if len(sys.argv) > 5 else (1024, 
 sc = fs.load(os.path.join(ROOT, "tests", "golden", "scenes", name + ".fscene.gz"))
 
 def run(env):
-    for k in ("BDPT_SCHED", "BDPT_WALK_CTAS", "BDPT_SHADOW_CTAS", "BDPT_VARIANT", "BDPT_CONNECT_MINB", "BDPT_BATCH_LOG2", "BDPT_BATCH_GIB", "BDPT_BVH_LEAF", "BDPT_BVH_CT", "BDPT_TOP_NODES", "BDPT_SPEC", "BDPT_PAD", "BDPT_SKEW"):
+    for k in ("BDPT_SCHED", "BDPT_WALK_CTAS", "BDPT_SHADOW_CTAS", "BDPT_VARIANT", "BDPT_CONNECT_MINB", "BDPT_BATCH_LOG2", "BDPT_BATCH_GIB", "BDPT_BVH_LEAF", "BDPT_BVH_CP", "BDPT_BVH_BINS", "BDPT_TOP_NODES", "BDPT_SPEC", "BDPT_PAD", "BDPT_SKEW"):
         os.environ.pop(k, None)
     os.environ.update({k: str(v) for k, v in env.items()})
     R = api.Renderer(0, ns_aa=spp, max_ray_depth=m, seed=1)
@@ -27,7 +27,7 @@ def run(env):
     return img
 
 base = run({})
-variants = [{"BDPT_SPEC": 0}, {"BDPT_SPEC": 5}]
+variants = [{"BDPT_SPEC": 0}, {"BDPT_SCHED": 0}, {"BDPT_BATCH_LOG2": 22, "BDPT_BATCH_GIB": 12}]
 for v in variants:
     img = run(v)
     d = np.abs(img - base)
