@@ -1,4 +1,6 @@
 import os
+
+import numpy as np
 import sys
 
 import pytest
@@ -22,6 +24,21 @@ def golden_dir():
 
 def load_scene(name):
     from bdpt import flatscene as fs
+    if name == "CBbunny_microfacet_cu":
+        # reference dae/sky/CBbunny_microfacet_cu.dae: byte for byte CBbunny.dae's geometry, camera and light with the
+        # bunny's material (index 0) a copper MicrofacetBSDF (eta, k, alpha from the file's CGL profile) — derived here
+        # instead of committing the 3.5 MB geometry twice; tests/test_host_loader.py checks the derivation against the
+        # .dae where the reference tree is mounted
+        sc = fs.load(os.path.join(GOLDEN, "scenes", "CBbunny.fscene.gz"))
+        mats = sc.materials.copy()
+        m = mats[0]
+        m["type"] = fs.MAT_MICROFACET
+        m["reflectance"] = 0.0
+        m["eta"] = [0.33228, 1.0162, 1.2474]
+        m["k"] = [3.1646, 2.5785, 2.4603]
+        m["alpha"] = np.float32(0.05)
+        mats[0] = m
+        return fs.FlatScene(sc.camera, mats, sc.lights, sc.prims)
     return fs.load(os.path.join(GOLDEN, "scenes", name + ".fscene.gz"))
 
 

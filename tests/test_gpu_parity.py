@@ -190,7 +190,9 @@ def test_strategy_images_match_oracle(api, O):
                                               # no reference behaviour exists for these two (the reference aborts on
                                               # microfacet MIS and leaves refraction's TIR outputs unset): the oracle
                                               # defines them (oracle/bdpt_oracle.cpp) and the CUDA path must agree
-                                              ("CBspheres_microfacet_al_ag", 5, 0), ("CBspheres_refract", 5, 0)])
+                                              ("CBspheres_microfacet_al_ag", 5, 0), ("CBspheres_refract", 5, 0),
+                                              # a deep BVH with a rough conductor on it (triangle trait, untraited materials)
+                                              ("CBbunny_microfacet_cu", 5, 0)])
 def test_render_matches_oracle_same_random_numbers(api, O, name, m, roulette):
     W, H, ns = 64, 48, 8
     R = make_renderer(api, name, W, H, ns_aa=ns, max_ray_depth=m, seed=11, roulette=bool(roulette))

@@ -22,6 +22,7 @@ CASES = {  # fixture name -> .dae file name(s) to look for
     "CBbunny": ["CBbunny.dae"],
     "CBcoil": ["CBcoil.dae"],
     "CBspheres_lambertian_occluded": ["../ben/CBspheres_lambertian.dae", "CBspheres_lambertian_occluded.dae"],
+    "CBbunny_microfacet_cu": ["CBbunny_microfacet_cu.dae"],     # fixture derived from CBbunny's, see conftest.load_scene
 }
 
 
