@@ -48,7 +48,7 @@ struct Builder {
   int kBins = 16;          // SAH bins per axis (BDPT_BVH_BINS, tuning only)
   static constexpr int kParallelMin = 2048;   // subtrees smaller than this are not worth a thread
   int kMaxLeaf = 3;        // primitives per leaf child (<= 3: the node's meta byte counts them in unary)
-  float kPrimCost = 0.4f;  // SAH cost of one primitive test relative to one visit of an 8-wide node
+  float kPrimCost = 0.8f;  // SAH cost of one primitive test relative to one visit of an 8-wide node (0.4 … 1.0: within 1.5 %)
 
   explicit Builder(const std::vector<BuildPrim>& p) : prims(p) {
     idx.resize(p.size());
