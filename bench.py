@@ -91,7 +91,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", os.environ.get("BENCH_SMI_MS", "200"), "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -331,6 +331,7 @@ def main():
                                     % (B, 64.0 * (verts + 1) * B / 1e9, 48.0 * shadow_per_sample * B / 1e9)},
             "mrays_per_s": value * rays_per_sample / 1e6, "rays_per_sample": rays_per_sample,
             "kernel_ms_first_batches": {**kern, "batches": tb, "batch_samples": B},
+            "render_ms_last_step": st["ms_total"],   # CUDA events around the batch loop inside bdpt_render (rank 0)
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_wall / args.steps},
             "gpu_launches": gpu_launches,
