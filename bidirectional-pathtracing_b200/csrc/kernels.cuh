@@ -365,17 +365,20 @@ __device__ inline void connect_strategies(const Job& J, const int si, const int 
       contrib = eye_alpha * Lv.alpha * (f_eye * f_light) * g;
       bool push = false;
       unsigned int target = pix_own;
+      // (for t = 1 the raster position is already known: a connection that leaves the frame never reaches the queue)
+      const bool in_frame = t != 1 || (eye_x >= 0 && eye_y >= 0 && eye_x < J.cam.W && eye_y < J.cam.H);
       const bool gate = norm(contrib) > BDPT_EPS_F;
+      const bool reserve = gate && in_frame;
       // The queue slot is reserved here, before the weight is known: the atomic's round trip to L2 (ncu put 23 % of
       // this kernel's stall samples on it) then overlaps the weight computation.  A connection that passes the gate
       // but ends up not pushed (weight 0 / NaN, or off-frame for t = 1: rare) fills its slot with a null ray.
       unsigned int r_active = 0u, r_mask = 0u, r_ticket = 0u;
       if (!TRACE) {
         r_active = __activemask();
-        r_mask = __ballot_sync(r_active, gate);
+        r_mask = __ballot_sync(r_active, reserve);
         if (r_mask != 0u && (int)(threadIdx.x & 31) == __ffs(r_mask) - 1) r_ticket = atomicAdd(J.qctr + 0, (unsigned int)__popc(r_mask));
       }
-      if (gate) {
+      if (gate && (TRACE || in_frame)) {   // (the trace hook records the weight of off-frame connections too)
         // ---- MIS weight (bidirection.cpp:121-293 in closed form, see header)
         double winv = 1.0;
         if (t >= 2) {
@@ -438,7 +441,7 @@ __device__ inline void connect_strategies(const Job& J, const int si, const int 
       } else if (r_mask != 0u) {
         const unsigned int lane = threadIdx.x & 31;
         const unsigned int base = __shfl_sync(r_active, r_ticket, __ffs(r_mask) - 1);
-        if (gate) {
+        if (reserve) {
           const unsigned int idx = base + __popc(r_mask & ((1u << lane) - 1u));
           if (idx >= J.qcap) J.qctr[2] = 1u;
           else {
@@ -515,8 +518,9 @@ __global__ void __launch_bounds__(128) k_shadow(const Job J) {
     unsigned int idx = base + lane;
     if (idx < n) {
       float4 a, b; ld256(J.q0 + 2 * (size_t)idx, &a, &b);
-      Hit h = traverse<true, TR>(J.sc, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), BDPT_EPS_F, a.w);
-      traced++;
+      const bool real = a.w >= 0.f;   // tmax < 0: a reserved slot whose connection turned out to carry nothing
+      Hit h; h.leaf = 0;
+      if (real) { h = traverse<true, TR>(J.sc, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), BDPT_EPS_F, a.w); traced++; }
       const unsigned clear = __ballot_sync(__activemask(), h.leaf < 0);
       if (h.leaf < 0) shadow_splat(J, clear, idx);
     }
@@ -589,8 +593,10 @@ __global__ void __launch_bounds__(128, MINB) k_shadow_pt(const Job J) {
       unsigned my = warp_fetch(J.qctr + 1, n, 256u, !active, wf);
       if (my != BDPT_NONE) {
         float4 a, b; ld256(J.q0 + 2 * (size_t)my, &a, &b);
-        T.begin(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), BDPT_EPS_F, a.w);
-        idx = my; active = true;
+        if (a.w >= 0.f) {   // tmax < 0: a reserved slot whose connection turned out to carry nothing
+          T.begin(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), BDPT_EPS_F, a.w);
+          idx = my; active = true;
+        }
       }
     }
     if (__ballot_sync(0xffffffffu, active) == 0u) {
