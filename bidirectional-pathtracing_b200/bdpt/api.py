@@ -24,6 +24,8 @@ LIB_PATH = os.path.join(PKG_DIR, "libbdpt_b200.so")
 BUFFER_SUM, BUFFER_EYE, BUFFER_LIGHT = 0, 1, 2
 FLAG_ROULETTE = 1
 FLAG_NO_MIS = 2
+FLAG_BALANCE = 4
+COMM_ID_BYTES = 128
 
 
 class BdptError(RuntimeError):
@@ -51,7 +53,9 @@ EXPORTS = ["bdpt_create", "bdpt_destroy", "bdpt_last_error", "bdpt_set_stream", 
            "bdpt_set_camera", "bdpt_set_frame", "bdpt_clear", "bdpt_render", "bdpt_read_framebuffer",
            "bdpt_framebuffer_device", "bdpt_tonemap_rgba8", "bdpt_get_stats", "bdpt_intersect_batch",
            "bdpt_occluded_batch", "bdpt_bsdf_eval_batch", "bdpt_bsdf_sample_batch", "bdpt_light_eval_batch",
-           "bdpt_camera_eval_batch", "bdpt_trace_sample", "bdpt_host_build_bvh"]
+           "bdpt_camera_eval_batch", "bdpt_trace_sample", "bdpt_host_build_bvh",
+           "bdpt_comm_unique_id", "bdpt_comm_init_rank", "bdpt_comm_init_all", "bdpt_reduce", "bdpt_reduce_all",
+           "bdpt_comm_destroy"]
 
 _lib = None
 
@@ -85,6 +89,12 @@ def load_library():
     L.bdpt_occluded_batch.argtypes = [vp, dp, C.c_size_t, C.POINTER(C.c_int32)]
     L.bdpt_trace_sample.argtypes = [vp, C.POINTER(RenderParams), C.c_int, C.c_int, C.c_int, dp, C.c_size_t,
                                     C.POINTER(C.c_size_t)]
+    L.bdpt_comm_unique_id.argtypes = [vp]
+    L.bdpt_comm_init_rank.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.bdpt_comm_init_all.argtypes = [C.POINTER(vp), C.c_int]
+    L.bdpt_reduce.argtypes = [vp, C.c_int]
+    L.bdpt_reduce_all.argtypes = [C.POINTER(vp), C.c_int, C.c_int]
+    L.bdpt_comm_destroy.argtypes = [vp]
     u32p = C.POINTER(C.c_uint32)
     L.bdpt_host_build_bvh.argtypes = [vp, C.c_uint32, u32p, C.c_uint32, u32p, u32p, u32p]
     for name in EXPORTS:
@@ -102,7 +112,7 @@ class Renderer:
     """One GPU, one scene, one frame.  Mirrors the reference's RaytracedRenderer for the BDPT path."""
 
     def __init__(self, device: int = 0, *, ns_aa: int = 1, max_ray_depth: int = 1, seed: int = 0,
-                 roulette: bool = False, no_mis: bool = False):
+                 roulette: bool = False, no_mis: bool = False, balance: bool = False):
         self.L = load_library()
         self.h = C.c_void_p()
         rc = self.L.bdpt_create(device, C.byref(self.h))
@@ -116,6 +126,8 @@ class Renderer:
         self.seed = seed
         self.roulette = roulette
         self.no_mis = no_mis
+        self.balance = balance      # Veach's balance heuristic instead of the reference's power heuristic (beta = 2)
+        self.device = device
         self.W = self.H = 0
         self._keep = None
 
@@ -163,7 +175,8 @@ class Renderer:
         p.max_ray_depth = self.max_ray_depth
         p.first_sample = first_sample
         p.n_samples = self.ns_aa if n_samples is None else n_samples
-        p.flags = (FLAG_ROULETTE if self.roulette else 0) | (FLAG_NO_MIS if self.no_mis else 0)
+        p.flags = ((FLAG_ROULETTE if self.roulette else 0) | (FLAG_NO_MIS if self.no_mis else 0) |
+                   (FLAG_BALANCE if self.balance else 0))
         p.only_t, p.only_s = strategy if strategy else (-1, -1)
         p.seed = self.seed
         return p
@@ -182,6 +195,15 @@ class Renderer:
         ptr, n = C.c_void_p(), C.c_size_t()
         self._ck(self.L.bdpt_framebuffer_device(self.h, which, C.byref(ptr), C.byref(n)))
         return ptr.value, n.value
+
+    # -- multi-GPU: one NCCL sum-reduce of the accumulators (eye + light, one allocation) to the root
+    def comm_init_rank(self, nranks: int, rank: int, id_bytes: bytes):
+        buf = C.create_string_buffer(bytes(id_bytes), COMM_ID_BYTES)
+        self._ck(self.L.bdpt_comm_init_rank(self.h, nranks, rank, C.cast(buf, C.c_void_p)))
+
+    def reduce(self, root: int = 0):
+        """Enqueues the reduce on the renderer's stream (after the renders issued so far)."""
+        self._ck(self.L.bdpt_reduce(self.h, root))
 
     def tonemap(self, which: int = BUFFER_SUM) -> np.ndarray:
         """(H, W, 4) uint8, row 0 = top (PNG order): the reference's toColor + save_image flip."""
@@ -233,6 +255,16 @@ class Renderer:
         verts = out[2:2 + 13 * (ne + nl)].reshape(-1, 13)
         strat = out[2 + 13 * (ne + nl):].reshape(-1, 8)
         return {"eye": verts[:ne], "light": verts[ne:], "strategies": strat}
+
+
+def comm_unique_id() -> bytes:
+    """A fresh NCCL id (rank 0 makes it, every rank passes it to Renderer.comm_init_rank)."""
+    L = load_library()
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    rc = L.bdpt_comm_unique_id(C.cast(buf, C.c_void_p))
+    if rc != 0:
+        raise BdptError(f"bdpt_comm_unique_id failed ({rc}): {L.bdpt_last_error(None).decode()}")
+    return buf.raw
 
 
 def host_build_bvh(scene: fs.FlatScene):

@@ -41,7 +41,11 @@ struct BdptContext {
   // frame
   int W = 0, H = 0;
   DCamera cam{};
-  float *acc_eye = nullptr, *acc_light = nullptr, *resolve_tmp = nullptr;
+  // un-normalised accumulators: ONE allocation of 2 * W * H float4 {r, g, b, -}, eye image first, light image second,
+  // so that a multi-GPU frame is reduced with a single collective (bdpt_reduce) and a splat is one 16-byte reduction
+  float4* acc = nullptr;
+  float4 *acc_eye = nullptr, *acc_light = nullptr;
+  float* resolve_tmp = nullptr;
   uint8_t* rgba_tmp = nullptr;
   int ns_last = 1;
 
@@ -50,29 +54,27 @@ struct BdptContext {
   char* slab = nullptr;        // backing store of v0..v3, q0..q2, counts
   size_t slab_bytes = 0, slab_sz_v = 0, slab_sz_q = 0;
   int slab_align_kb = 2048;    // BDPT_SLAB_ALIGN_KB, tuning only
-  float4 *v0 = nullptr, *v1 = nullptr, *v2 = nullptr, *v3 = nullptr, *q0 = nullptr, *q1 = nullptr, *q2 = nullptr;
+  float4 *v0 = nullptr, *q0 = nullptr, *q2 = nullptr;
   int* counts = nullptr;
   char* counters = nullptr;    // 2 MiB block holding qctr and d_stats
   unsigned int* qctr = nullptr;
   unsigned long long* d_stats = nullptr;
   unsigned int* h_qctr = nullptr;  // pinned
-  // wavefront walk (sched == 2)
-  WfBuf wf{}; size_t wf_cap = 0; int wf_cap_m = -1;
 
   // stats
   BdptStats stats{};
   std::vector<cudaEvent_t> ev;
   int sm_count = 148;
-  // walk scheduler: 0 = one subpath per lane, 1 = persistent per-lane state machine, 2 = per-bounce wavefront
-  // (measured slower: its state round-trips cost more HBM time than the divergence it removes); -1 = choose by
-  // BVH size at upload (tiny trees have no traversal divergence to hide).  Override: BDPT_SCHED.
+  // walk scheduler: 0 = one subpath per lane, 1 = persistent per-lane state machine; -1 = choose by BVH size at
+  // upload (tiny trees have no traversal divergence to hide).  Override: BDPT_SCHED.  (A per-bounce wavefront walk
+  // was measured in round 1 and removed: its state round trips cost more HBM time than the divergence it removed.)
   int sched = -1, sched_req = -1;
   int variant = 0;      // k_walk_pt build: 0 = 6 CTAs/SM (default), 1 = 4 CTAs/SM without spills (BDPT_VARIANT, tuning only)
   // BVH nodes the persistent kernels stage in shared memory (BDPT_TOP_NODES; 73 = root + 8 + 64 = three levels).
   // Off by default: measured on B200 it changes nothing (-0.5 % at 73, -1.6 % at 300) — L1 already holds the top
   // of the tree (77 % L1 hit rate in k_walk_pt).
   int top_nodes = 0;
-  int connect_minb = 6; // __launch_bounds__ min blocks of k_connect (BDPT_CONNECT_MINB, tuning only)
+  int connect_minb = 0; // __launch_bounds__ min blocks of k_connect: 0 = the build's own (BDPT_CONNECT_MINB, tuning only)
   int traits = 0;       // BDPT_TRAIT_* of the uploaded scene
   int point_lights = 0; // the uploaded scene has a point light
   int spec = 7;         // which kernels may use their trait-specialised build: 1 walk, 2 connect, 4 shadow (BDPT_SPEC, tuning only)
@@ -81,6 +83,8 @@ struct BdptContext {
   // 180 GB are there to be used.  Storage is only ever allocated for the samples a render actually has.
   int batch_log2 = 24, batch_gib = 48;
   int walk_ctas = 6, shadow_ctas = 0;  // resident CTAs per SM of the persistent kernels (shadow: 0 = the build's own, 10 or 8)
+  // multi-GPU (comm.inc): an ncclComm_t, bound at run time
+  void* comm = nullptr; int comm_ranks = 0, comm_rank = 0;
 };
 
 namespace {
@@ -162,9 +166,9 @@ void carve_slab(BdptContext* ctx, char* slab) {
   const size_t sz_v = ctx->slab_sz_v, sz_q = ctx->slab_sz_q;
   // one 64-byte record per vertex (v0..v3 are its four float4): a lane's four stores in the walk fill two whole
   // 32-byte sectors (as four separate planes they were partial-sector writes and DRAM saw 2x the bytes)
-  ctx->v0 = (float4*)base; ctx->v1 = ctx->v0 + 1; ctx->v2 = ctx->v0 + 2; ctx->v3 = ctx->v0 + 3;
-  // shadow queue: 32-byte ray records {q0, q1} interleaved (q1 = q0 + 1, stride 2), contributions q2 as a plane
-  ctx->q0 = (float4*)(base + 4 * sz_v); ctx->q1 = ctx->q0 + 1; ctx->q2 = (float4*)(base + 4 * sz_v + 2 * sz_q);
+  ctx->v0 = (float4*)base;
+  // shadow queue: 32-byte ray records (q0, stride 2), contributions q2 as a plane
+  ctx->q0 = (float4*)(base + 4 * sz_v); ctx->q2 = (float4*)(base + 4 * sz_v + 2 * sz_q);
   ctx->counts = (int*)(base + 4 * sz_v + 3 * sz_q);
 }
 
@@ -175,7 +179,7 @@ int ensure_batch_storage(BdptContext* ctx, size_t B, int m, size_t qcap) {
     // apart is what spreads a warp's loads over the HBM channels.)
     const size_t nB = std::max(B, ctx->cap_B); const int nm = std::max(m, ctx->cap_m); const size_t nq = std::max(qcap, ctx->cap_q);
     dfree(ctx->slab);
-    ctx->v0 = ctx->v1 = ctx->v2 = ctx->v3 = nullptr; ctx->q0 = ctx->q1 = ctx->q2 = nullptr; ctx->counts = nullptr;
+    ctx->v0 = nullptr; ctx->q0 = ctx->q2 = nullptr; ctx->counts = nullptr;
     ctx->cap_B = 0; ctx->cap_m = -1; ctx->cap_q = 0;   // nothing is held until the allocation below succeeds
     const size_t n = 2 * (size_t)(nm + 1) * nB;
     const size_t align = (size_t)ctx->slab_align_kb << 10;
@@ -187,18 +191,6 @@ int ensure_batch_storage(BdptContext* ctx, size_t B, int m, size_t qcap) {
     carve_slab(ctx, ctx->slab);
     ctx->cap_B = nB; ctx->cap_m = nm; ctx->cap_q = nq;
   }
-  if (ctx->sched == 2 && (2 * B > ctx->wf_cap || m > ctx->wf_cap_m)) {
-    WfBuf& F = ctx->wf;
-    dfree(F.r0); dfree(F.r1); dfree(F.h); dfree(F.s0); dfree(F.s1); dfree(F.s2); dfree(F.s3); dfree(F.s4);
-    dfree(F.queue_a); dfree(F.queue_b); dfree(F.ctr);
-    size_t n = std::max(2 * B, ctx->wf_cap); int nm = std::max(m, ctx->wf_cap_m);
-    float4** planes[8] = {&F.r0, &F.r1, &F.h, &F.s0, &F.s1, &F.s2, &F.s3, &F.s4};
-    for (auto pp : planes) CK(cudaMalloc(pp, n * sizeof(float4)));
-    CK(cudaMalloc(&F.queue_a, n * sizeof(unsigned int)));
-    CK(cudaMalloc(&F.queue_b, n * sizeof(unsigned int)));
-    CK(cudaMalloc(&F.ctr, 4 * (size_t)(nm + 3) * sizeof(unsigned int)));
-    ctx->wf_cap = n; ctx->wf_cap_m = nm;
-  }
   if (!ctx->qctr) {
     // The queue counter is the hottest address of k_connect (one returning atomic per warp and strategy, ~12 M per
     // batch).  As a 16-byte cudaMalloc it shared a small-allocation page with the materials, the lights and the
@@ -209,7 +201,8 @@ int ensure_batch_storage(BdptContext* ctx, size_t B, int m, size_t qcap) {
     ctx->qctr = (unsigned int*)ctx->counters;
     ctx->d_stats = (unsigned long long*)(ctx->counters + ((size_t)1 << 20));
     CK(cudaMemset(ctx->d_stats, 0, 4 * sizeof(unsigned long long)));
-    CK(cudaMallocHost(&ctx->h_qctr, 4 * sizeof(unsigned int)));
+    CK(cudaMemset(ctx->qctr, 0, 8 * sizeof(unsigned int)));
+    CK(cudaMallocHost(&ctx->h_qctr, 8 * sizeof(unsigned int)));
   }
   return BDPT_OK;
 }
@@ -222,8 +215,8 @@ cudaEvent_t get_event(BdptContext* ctx, size_t i) {
 void fill_job(BdptContext* ctx, const BdptRenderParams* p, Job* J) {
   memset(J, 0, sizeof(Job));
   J->sc = ctx->sc; J->cam = ctx->cam; J->point_lights = ctx->point_lights;
-  J->v0 = ctx->v0; J->v1 = ctx->v1; J->v2 = ctx->v2; J->v3 = ctx->v3; J->counts = ctx->counts;
-  J->q0 = ctx->q0; J->q1 = ctx->q1; J->q2 = ctx->q2; J->qctr = ctx->qctr; J->qcap = (unsigned int)ctx->cap_q;
+  J->v0 = ctx->v0; J->counts = ctx->counts;
+  J->q0 = ctx->q0; J->q2 = ctx->q2; J->qctr = ctx->qctr; J->qcap = (unsigned int)ctx->cap_q;
   J->acc_eye = ctx->acc_eye; J->acc_light = ctx->acc_light; J->stats = ctx->d_stats; J->dbg = nullptr;
   // the walk stores a vertex before it tests the depth (bidirection.cpp:82-86): m = 0 behaves as m = 1
   J->seed = p->seed; J->m = std::max(1, p->max_ray_depth); J->first_sample = p->first_sample;
@@ -232,38 +225,40 @@ void fill_job(BdptContext* ctx, const BdptRenderParams* p, Job* J) {
   J->div_tiles_x = make_fastdiv((uint32_t)J->tiles_x); J->div_npix_pad = make_fastdiv((uint32_t)J->npix_pad);
   J->roulette = (p->flags & BDPT_FLAG_ROULETTE) ? 1 : 0;
   J->no_mis = (p->flags & BDPT_FLAG_NO_MIS) ? 1 : 0;
+  J->balance = (p->flags & BDPT_FLAG_BALANCE) ? 1 : 0;
   J->ntop = std::min(ctx->top_nodes, ctx->sc.n_nodes);
   J->only_t = p->only_t; J->only_s = p->only_s;
   J->single_x = -1; J->single_y = -1;
 }
 
+// Launches k_connect in the build the scene's traits allow (the trait never depends on the tuning knob).
+template <bool TRACE, int TR>
+void launch_connect(BdptContext* ctx, const Job& J, unsigned grid, int minb) {
+  constexpr int NT = BDPT_CONNECT_NT;
+  switch (minb) {
+    case 3: k_connect<TRACE, 3, TR><<<grid, NT, 0, ctx->stream>>>(J); break;
+    case 4: k_connect<TRACE, 4, TR><<<grid, NT, 0, ctx->stream>>>(J); break;
+    case 5: k_connect<TRACE, 5, TR><<<grid, NT, 0, ctx->stream>>>(J); break;
+    case 8: k_connect<TRACE, 8, TR><<<grid, NT, 0, ctx->stream>>>(J); break;
+    default: k_connect<TRACE, 6, TR><<<grid, NT, 0, ctx->stream>>>(J); break;
+  }
+}
+
 // Runs one batch on ctx->stream.  evbase >= 0: record 4 events around the three kernels.
 template <bool TRACE>
 int run_batch(BdptContext* ctx, Job& J, long evbase) {
+  // queue tail, shadow cursor, walk cursor; the overflow flag (word 4) is per render
   CK(cudaMemsetAsync(ctx->qctr, 0, 4 * sizeof(unsigned int), ctx->stream));
   const int threads = 128;
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 0), ctx->stream);
-  if (ctx->sched == 2) {
-    // wavefront walk: generate, then per bounce trace + shade (2m + 1 launches)
-    WfBuf F = ctx->wf;
-    unsigned int* ctr0 = F.ctr;
-    CK(cudaMemsetAsync(ctr0, 0, 4 * (size_t)(J.m + 3) * sizeof(unsigned int), ctx->stream));
-    const unsigned n2 = 2u * (unsigned)J.B;
-    k_wf_gen<<<(n2 + threads - 1) / threads, threads, 0, ctx->stream>>>(J, F);
-    for (int b = 0; b < J.m; b++) {
-      F.ctr = ctr0 + 4 * b;
-      k_wf_trace<<<ctx->sm_count * (ctx->shadow_ctas > 0 ? ctx->shadow_ctas : 8), threads, 0, ctx->stream>>>(J, F, b == 0 ? n2 : 0u);
-      k_wf_shade<<<(n2 + threads - 1) / threads, threads, 0, ctx->stream>>>(J, F, b == 0 ? n2 : 0u);
-      std::swap(F.queue_a, F.queue_b);   // this bounce's survivors are the next bounce's input
-    }
-    ctx->stats.kernel_launches += 2 * J.m;
-  } else if (ctx->sched) {
+  const int wtr = (ctx->spec & 1) ? ctx->traits : 0;
+  if (ctx->sched) {
     const int g = ctx->sm_count * ctx->walk_ctas;
     // 6 CTAs/SM (80 registers, ~0.2 KB of spills) beats 4 CTAs at 101 registers by 6 %: the state machine is
     // latency-bound between votes.  BDPT_VARIANT=1 selects the unspilled build for comparison.
     const size_t shm = (size_t)J.ntop * 80;
     if (ctx->variant == 1) k_walk_pt<16, 8, 4><<<g, threads, shm, ctx->stream>>>(J);
-    else switch ((ctx->spec & 1) ? ctx->traits : 0) {
+    else switch (wtr) {
       case 1: k_walk_pt<14, 6, 6, 1><<<g, threads, shm, ctx->stream>>>(J); break;
       case 2: k_walk_pt<14, 6, 6, 2><<<g, threads, shm, ctx->stream>>>(J); break;
       case 3: k_walk_pt<14, 6, 6, 3><<<g, threads, shm, ctx->stream>>>(J); break;
@@ -271,10 +266,9 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
       case 5: k_walk_pt<14, 6, 6, 5><<<g, threads, shm, ctx->stream>>>(J); break;
       default: k_walk_pt<14, 6, 6, 0><<<g, threads, shm, ctx->stream>>>(J); break;
     }
-  }
-  else {
+  } else {
     const unsigned g = (unsigned)((2 * J.B + threads - 1) / threads);
-    switch ((ctx->spec & 1) ? ctx->traits : 0) {
+    switch (wtr) {
       case 1: k_walk<1><<<g, threads, 0, ctx->stream>>>(J); break;
       case 2: k_walk<2><<<g, threads, 0, ctx->stream>>>(J); break;
       case 3: k_walk<3><<<g, threads, 0, ctx->stream>>>(J); break;
@@ -284,32 +278,17 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
     }
   }
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 1), ctx->stream);
-  const unsigned cgrid = (unsigned)((J.B + threads - 1) / threads) * (unsigned)(J.m + 1);
-  const bool lambert = !TRACE && (ctx->spec & 2) && (ctx->traits & BDPT_TRAIT_LAMBERT);
-  // The Lambert build needs 96 registers unspilled and runs best that way (5 CTAs/SM); forced to 80 registers it is
-  // slower than the generic build at 80, which tolerates its spills (measured: 6.3 / 9.7 / 7.2 ms per 2^24 samples).
-  // The no-microfacet build likewise: 6.3 ms at 96 registers (bounds 5), 7.3 at 103 (bounds 4), 9.7 at 80 (bounds 6);
-  // the generic build 7.1 at 80.
-  const bool nomf = !TRACE && (ctx->spec & 2) && (ctx->traits & BDPT_TRAIT_NOMF);
-  switch (TRACE ? 0 : (ctx->connect_minb != 6 ? ctx->connect_minb : lambert ? 4 : nomf ? 5 : 6)) {
-    case 4:
-      if (lambert) k_connect<TRACE, 4, BDPT_TRAIT_LAMBERT><<<cgrid, threads, 0, ctx->stream>>>(J);
-      else k_connect<TRACE, 4><<<cgrid, threads, 0, ctx->stream>>>(J);
-      break;
-    case 5: k_connect<TRACE, 5, BDPT_TRAIT_NOMF><<<cgrid, threads, 0, ctx->stream>>>(J); break;
-    case 6:
-      if (lambert) k_connect<TRACE, 6, BDPT_TRAIT_LAMBERT><<<cgrid, threads, 0, ctx->stream>>>(J);
-      else k_connect<TRACE, 6><<<cgrid, threads, 0, ctx->stream>>>(J);
-      break;
-    case 8:
-      if (lambert) k_connect<TRACE, 8, BDPT_TRAIT_LAMBERT><<<cgrid, threads, 0, ctx->stream>>>(J);
-      else k_connect<TRACE, 8><<<cgrid, threads, 0, ctx->stream>>>(J);
-      break;
-    default: k_connect<TRACE, 3><<<cgrid, threads, 0, ctx->stream>>>(J); break;
-  }
+  // k_connect: the Lambert build needs ~96 registers unspilled and runs best that way; the generic build tolerates
+  // its spills at 80 registers / 6 CTAs per SM (round 1 measurements; BDPT_CONNECT_MINB overrides the bound only)
+  const unsigned cgrid = (unsigned)((J.B + BDPT_CONNECT_NT - 1) / BDPT_CONNECT_NT);
+  const int ctr = (!TRACE && (ctx->spec & 2)) ? (ctx->traits & (BDPT_TRAIT_LAMBERT | BDPT_TRAIT_NOMF)) : 0;
+  if (ctr & BDPT_TRAIT_LAMBERT) launch_connect<TRACE, BDPT_TRAIT_LAMBERT>(ctx, J, cgrid, ctx->connect_minb ? ctx->connect_minb : 4);
+  else if (ctr & BDPT_TRAIT_NOMF) launch_connect<TRACE, BDPT_TRAIT_NOMF>(ctx, J, cgrid, ctx->connect_minb ? ctx->connect_minb : 5);
+  else launch_connect<TRACE, 0>(ctx, J, cgrid, ctx->connect_minb ? ctx->connect_minb : 6);
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 2), ctx->stream);
-  if (ctx->sched || ctx->sched_req < 0) {   // the persistent form wins even on one-node BVHs (2.9 vs 4.9 ms per 2^24 samples)
-    // triangles only: 48 registers (28 B of spills) and 10 CTAs/SM; with the sphere test compiled in, 64 and 8
+  {
+    // triangles only: 48 registers (28 B of spills) and 10 CTAs/SM; with the sphere test compiled in, 64 and 8.
+    // (The persistent form wins even on one-node BVHs: 2.9 vs 4.9 ms per 2^24 samples.)
     const size_t shm = (size_t)J.ntop * 80;
     if ((ctx->spec & 4) && (ctx->traits & BDPT_TRAIT_TRIS)) {
       const int c = ctx->shadow_ctas > 0 ? ctx->shadow_ctas : 10;
@@ -319,8 +298,6 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
       k_shadow_pt<8><<<ctx->sm_count * c, threads, shm, ctx->stream>>>(J);
     }
   }
-  else if ((ctx->spec & 4) && (ctx->traits & BDPT_TRAIT_TRIS)) k_shadow<BDPT_TRAIT_TRIS><<<ctx->sm_count * 8, threads, 0, ctx->stream>>>(J);
-  else k_shadow<0><<<ctx->sm_count * 8, threads, 0, ctx->stream>>>(J);
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 3), ctx->stream);
   ctx->stats.kernel_launches += 3;
   CK(cudaGetLastError());
@@ -377,7 +354,7 @@ int bdpt_create(int device, BdptContext** out) {
   if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return BDPT_ERR_CUDA; }
   ctx->own_stream = true;
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
-  if (const char* e = getenv("BDPT_SCHED")) ctx->sched_req = atoi(e);
+  if (const char* e = getenv("BDPT_SCHED")) ctx->sched_req = std::min(1, atoi(e));
   ctx->sched = ctx->sched_req >= 0 ? ctx->sched_req : 1;
   if (const char* e = getenv("BDPT_BATCH_LOG2")) ctx->batch_log2 = std::min(24, std::max(10, atoi(e)));
   if (const char* e = getenv("BDPT_BATCH_GIB")) ctx->batch_gib = std::min(64, std::max(1, atoi(e)));
@@ -394,12 +371,12 @@ int bdpt_create(int device, BdptContext** out) {
 
 void bdpt_destroy(BdptContext* ctx) {
   if (!ctx) return;
+  bdpt_comm_destroy(ctx);
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   dfree(ctx->d_nodes); dfree(ctx->d_prims); dfree(ctx->d_shading); dfree(ctx->d_mats); dfree(ctx->d_lights); dfree(ctx->d_prims64);
-  dfree(ctx->acc_eye); dfree(ctx->acc_light); dfree(ctx->resolve_tmp); dfree(ctx->rgba_tmp);
+  dfree(ctx->acc); dfree(ctx->resolve_tmp); dfree(ctx->rgba_tmp);
   dfree(ctx->slab); dfree(ctx->counters); ctx->qctr = nullptr; ctx->d_stats = nullptr;
-  { WfBuf& F = ctx->wf; dfree(F.r0); dfree(F.r1); dfree(F.h); dfree(F.s0); dfree(F.s1); dfree(F.s2); dfree(F.s3); dfree(F.s4); dfree(F.queue_a); dfree(F.queue_b); dfree(F.ctr); }
   if (ctx->h_qctr) cudaFreeHost(ctx->h_qctr);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -549,12 +526,19 @@ int bdpt_set_frame(BdptContext* ctx, int width, int height) {
   CK(cudaSetDevice(ctx->device));
   if (width != ctx->W || height != ctx->H) {
     CK(cudaStreamSynchronize(ctx->stream));
-    dfree(ctx->acc_eye); dfree(ctx->acc_light); dfree(ctx->resolve_tmp); dfree(ctx->rgba_tmp);
-    size_t n = (size_t)width * height * 3;
-    CK(cudaMalloc(&ctx->acc_eye, n * sizeof(float)));
-    CK(cudaMalloc(&ctx->acc_light, n * sizeof(float)));
-    CK(cudaMalloc(&ctx->resolve_tmp, n * sizeof(float)));
-    CK(cudaMalloc(&ctx->rgba_tmp, (size_t)width * height * 4));
+    // no frame is held until every allocation below has succeeded
+    ctx->W = ctx->H = 0;
+    dfree(ctx->acc); ctx->acc_eye = ctx->acc_light = nullptr;
+    dfree(ctx->resolve_tmp); dfree(ctx->rgba_tmp);
+    const size_t npix = (size_t)width * height;
+    cudaError_t e = cudaMalloc(&ctx->acc, 2 * npix * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->resolve_tmp, npix * 3 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->rgba_tmp, npix * 4);
+    if (e != cudaSuccess) {
+      dfree(ctx->acc); dfree(ctx->resolve_tmp); dfree(ctx->rgba_tmp);
+      return fail(ctx, BDPT_ERR_CUDA, std::string("frame buffers: ") + cudaGetErrorString(e));
+    }
+    ctx->acc_eye = ctx->acc; ctx->acc_light = ctx->acc + npix;
     ctx->W = width; ctx->H = height;
   }
   make_dcamera(ctx->cam_base, ctx->W, ctx->H, &ctx->cam);
@@ -564,11 +548,8 @@ int bdpt_set_frame(BdptContext* ctx, int width, int height) {
 int bdpt_clear(BdptContext* ctx) {
   if (!ctx) return BDPT_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
-  if (ctx->acc_eye) {
-    size_t n = (size_t)ctx->W * ctx->H * 3 * sizeof(float);
-    CK(cudaMemsetAsync(ctx->acc_eye, 0, n, ctx->stream));
-    CK(cudaMemsetAsync(ctx->acc_light, 0, n, ctx->stream));
-  }
+  if (ctx->acc && ctx->W > 0)
+    CK(cudaMemsetAsync(ctx->acc, 0, 2 * (size_t)ctx->W * ctx->H * sizeof(float4), ctx->stream));
   if (ctx->d_stats) CK(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
   BdptStats z{};
   z.ms_bvh_build = ctx->ms_bvh_build; z.bvh_nodes = ctx->bvh_nodes;
@@ -613,13 +594,14 @@ int bdpt_render(BdptContext* ctx, const BdptRenderParams* p) {
   const long timed = (long)std::min<unsigned long long>(n_batches, 64);
   cudaEvent_t e0 = get_event(ctx, 0), e1 = get_event(ctx, 1);
   CK(cudaEventRecord(e0, ctx->stream));
+  CK(cudaMemsetAsync(ctx->qctr + 4, 0, sizeof(unsigned int), ctx->stream));   // queue overflow: sticky over the batches
   for (unsigned long long b = 0; b < n_batches; b++) {
     J.g0 = b * B;
     J.k0 = (unsigned int)(J.g0 / (unsigned long long)npix_pad); J.p0 = (unsigned int)(J.g0 % (unsigned long long)npix_pad);
     rc = run_batch<false>(ctx, J, b < (unsigned long long)timed ? 2 + 4 * (long)b : -1);
     if (rc) return rc;
   }
-  CK(cudaMemcpyAsync(ctx->h_qctr, ctx->qctr, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_qctr, ctx->qctr, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaEventRecord(e1, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   float ms = 0;
@@ -636,34 +618,35 @@ int bdpt_render(BdptContext* ctx, const BdptRenderParams* p) {
   ctx->stats.timed_batches = (uint32_t)timed; ctx->stats.n_batches = (uint32_t)n_batches;
   ctx->stats.batch_samples = (uint32_t)B;
   ctx->stats.samples += (unsigned long long)ctx->W * ctx->H * (unsigned long long)p->n_samples;
-  if (ctx->h_qctr[2]) return fail(ctx, BDPT_ERR_OVERFLOW, "shadow queue overflow");
+  if (ctx->h_qctr[4]) return fail(ctx, BDPT_ERR_OVERFLOW, "shadow queue overflow");
   return BDPT_OK;
 }
 
 int bdpt_framebuffer_device(BdptContext* ctx, int which, void** device_ptr, size_t* n_floats) {
-  if (!ctx || !device_ptr || (which != BDPT_BUFFER_EYE && which != BDPT_BUFFER_LIGHT))
-    return ctx ? fail(ctx, BDPT_ERR_ARG, "only the eye and light accumulators exist on the device (sum = eye + light)") : BDPT_ERR_ARG;
-  if (!ctx->acc_eye) return fail(ctx, BDPT_ERR_ARG, "no frame size set");
-  *device_ptr = which == BDPT_BUFFER_EYE ? ctx->acc_eye : ctx->acc_light;
-  if (n_floats) *n_floats = (size_t)ctx->W * ctx->H * 3;
+  if (!ctx || !device_ptr || which < BDPT_BUFFER_SUM || which > BDPT_BUFFER_LIGHT) return BDPT_ERR_ARG;
+  if (!ctx->acc) return fail(ctx, BDPT_ERR_ARG, "no frame size set");
+  const size_t n = (size_t)ctx->W * ctx->H * 4;
+  // BDPT_BUFFER_SUM names the whole allocation (eye image then light image): what a single collective reduces
+  *device_ptr = which == BDPT_BUFFER_LIGHT ? ctx->acc_light : ctx->acc_eye;
+  if (n_floats) *n_floats = which == BDPT_BUFFER_SUM ? 2 * n : n;
   return BDPT_OK;
 }
 
 int bdpt_read_framebuffer(BdptContext* ctx, int which, float* rgb_out) {
   if (!ctx || !rgb_out || which < 0 || which > 2) return BDPT_ERR_ARG;
-  if (!ctx->acc_eye) return fail(ctx, BDPT_ERR_ARG, "no frame size set");
+  if (!ctx->acc) return fail(ctx, BDPT_ERR_ARG, "no frame size set");
   CK(cudaSetDevice(ctx->device));
-  size_t n = (size_t)ctx->W * ctx->H * 3;
-  k_resolve<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->acc_eye, ctx->acc_light, which, 1.0f / (float)ctx->ns_last, n, ctx->resolve_tmp);
+  const size_t npix = (size_t)ctx->W * ctx->H;
+  k_resolve<<<(unsigned)((npix + 255) / 256), 256, 0, ctx->stream>>>(ctx->acc_eye, ctx->acc_light, which, 1.0f / (float)ctx->ns_last, npix, ctx->resolve_tmp);
   ctx->stats.kernel_launches += 1;
-  CK(cudaMemcpyAsync(rgb_out, ctx->resolve_tmp, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(rgb_out, ctx->resolve_tmp, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return BDPT_OK;
 }
 
 int bdpt_tonemap_rgba8(BdptContext* ctx, int which, uint8_t* rgba_out) {
   if (!ctx || !rgba_out || which < 0 || which > 2) return BDPT_ERR_ARG;
-  if (!ctx->acc_eye) return fail(ctx, BDPT_ERR_ARG, "no frame size set");
+  if (!ctx->acc) return fail(ctx, BDPT_ERR_ARG, "no frame size set");
   CK(cudaSetDevice(ctx->device));
   int n = ctx->W * ctx->H;
   k_tonemap<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->acc_eye, ctx->acc_light, which, 1.0f / (float)ctx->ns_last, ctx->W, ctx->H, ctx->rgba_tmp);
@@ -796,8 +779,8 @@ int bdpt_trace_sample(BdptContext* ctx, const BdptRenderParams* p, int x, int y,
   rc = ensure_batch_storage(ctx, B, m, B * (size_t)(m + 1) * (size_t)(m + 1));
   if (rc) return rc;
   // the trace must not disturb the frame: render into scratch accumulators
-  float *se = nullptr, *sl = nullptr; double* dbg = nullptr;
-  size_t nacc = (size_t)ctx->W * ctx->H * 3 * sizeof(float);
+  float4 *se = nullptr, *sl = nullptr; double* dbg = nullptr;
+  size_t nacc = (size_t)ctx->W * ctx->H * sizeof(float4);
   size_t ndbg = (size_t)(m + 1) * (m + 2) * 8;
   CK(cudaMalloc(&se, nacc)); CK(cudaMalloc(&sl, nacc)); CK(cudaMalloc(&dbg, ndbg * sizeof(double)));
   CK(cudaMemsetAsync(se, 0, nacc, ctx->stream)); CK(cudaMemsetAsync(sl, 0, nacc, ctx->stream));
@@ -824,7 +807,7 @@ int bdpt_trace_sample(BdptContext* ctx, const BdptRenderParams* p, int x, int y,
   if (e != cudaSuccess) return fail(ctx, BDPT_ERR_CUDA, cudaGetErrorString(e));
 
   std::vector<double> rec;
-  const int nE = hc[0], nL = hc[B];
+  const int nE = hc[0] & 0xff, nL = hc[B] & 0xff;   // (bit 8: the subpath ends on an emitter)
   rec.push_back(nE + 1); rec.push_back(nL + 1);
   const double nan = NAN;
   for (int kind = 0; kind < 2; kind++) {
@@ -859,3 +842,5 @@ int bdpt_trace_sample(BdptContext* ctx, const BdptRenderParams* p, int x, int y,
 }
 
 }  // extern "C"
+
+#include "comm.inc"

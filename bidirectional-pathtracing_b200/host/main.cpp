@@ -6,8 +6,9 @@
 // worker threads); -l -a -b -d -H -c are accepted and ignored exactly as the reference's BDPT ignores
 // them; -e (environment map) and -p (cell render) are rejected: the reference's BDPT aborts on
 // environment lights (environment_light.cpp:182-208) and the cell path belongs to the GUI.
-// Extra options of this build: -g N (use N GPUs of this box, samples sharded), -S seed, -R (enable the
-// roulette rule the reference ships commented out), -o scene.fscene (dump the flat scene and exit).
+// Extra options of this build: -g N (use N GPUs of this box: samples sharded, scene ingested per GPU in parallel
+// host threads, ONE ncclReduce of the accumulators to GPU 0), -S seed, -R (enable the roulette rule the reference ships
+// commented out), -B (balance heuristic), -o scene.fscene (dump the flat scene and exit).
 // Output: out.png (toColor: exposure sqrt(2), gamma 2.2) and out_rate.png like the reference.
 #include <unistd.h>
 
@@ -36,6 +37,7 @@ static void usage(const char* bin) {
   printf("  -g  <INT>        Number of GPUs to shard the samples over (default 1)\n");
   printf("  -S  <INT>        Random seed (default 0)\n");
   printf("  -R               Russian roulette (off in the reference)\n");
+  printf("  -B               Balance heuristic for MIS (the reference uses the power heuristic, beta = 2)\n");
   printf("  -o  <FILENAME>   Write the flat scene (.fscene) and exit\n");
   printf("  -h               Print this help message\n\n");
 }
@@ -43,11 +45,11 @@ static void usage(const char* bin) {
 #define MSG(...) do { fprintf(stderr, "[PathTracer] "); fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); } while (0)
 
 int main(int argc, char** argv) {
-  int ns = 1, m = 1, threads = 1, W = 0, H = 0, gpus = 1, roulette = 0;
+  int ns = 1, m = 1, threads = 1, W = 0, H = 0, gpus = 1, roulette = 0, balance = 0;
   unsigned long long seed = 0;
   std::string out_png, out_fscene;
   int opt;
-  while ((opt = getopt(argc, argv, "s:l:t:m:e:hH:f:r:c:b:d:a:p:g:S:Ro:")) != -1) {
+  while ((opt = getopt(argc, argv, "s:l:t:m:e:hH:f:r:c:b:d:a:p:g:S:RBo:")) != -1) {
     switch (opt) {
       case 'f': out_png = optarg; break;
       case 'r': W = atoi(argv[optind - 1]); H = optind < argc ? atoi(argv[optind]) : 0; optind++; break;
@@ -57,6 +59,7 @@ int main(int argc, char** argv) {
       case 'g': gpus = atoi(optarg); break;
       case 'S': seed = strtoull(optarg, nullptr, 10); break;
       case 'R': roulette = 1; break;
+      case 'B': balance = 1; break;
       case 'o': out_fscene = optarg; break;
       case 'l': case 'c': case 'b': case 'd': break;        // no effect on the BDPT image
       case 'a': optind++; break;                              // two arguments, ignored
@@ -89,57 +92,50 @@ int main(int argc, char** argv) {
   if (gpus < 1) gpus = 1;
   MSG("Rendering on %d GPU%s (-t %d accepted and unused)", gpus, gpus > 1 ? "s" : "", threads);
 
+  // one context per GPU; the scene is replicated, every GPU ingests its copy in its own host thread
   std::vector<BdptContext*> ctx(gpus, nullptr);
-  for (int g = 0; g < gpus; g++) {
+  std::vector<int> rcs(gpus, 0);
+  for (int g = 0; g < gpus; g++)
     if (bdpt_create(g, &ctx[g]) != BDPT_OK) { MSG("Error: %s", bdpt_last_error(nullptr)); return 1; }
-    int rc = bdpt_upload_scene(ctx[g], &scene.camera, scene.materials.data(), (uint32_t)scene.materials.size(), scene.lights.data(),
-                               (uint32_t)scene.lights.size(), scene.prims.data(), (uint32_t)scene.prims.size());
-    if (rc == BDPT_OK) rc = bdpt_set_frame(ctx[g], W, H);
-    if (rc != BDPT_OK) { MSG("Error: %s", bdpt_last_error(ctx[g])); return 1; }
+  {
+    std::vector<std::thread> th;
+    for (int g = 0; g < gpus; g++)
+      th.emplace_back([&, g]() {
+        int rc = bdpt_upload_scene(ctx[g], &scene.camera, scene.materials.data(), (uint32_t)scene.materials.size(), scene.lights.data(),
+                                   (uint32_t)scene.lights.size(), scene.prims.data(), (uint32_t)scene.prims.size());
+        if (rc == BDPT_OK) rc = bdpt_set_frame(ctx[g], W, H);
+        rcs[g] = rc;
+      });
+    for (auto& t : th) t.join();
   }
+  for (int g = 0; g < gpus; g++) if (rcs[g] != BDPT_OK) { MSG("Error: %s", bdpt_last_error(ctx[g])); return 1; }
+  if (gpus > 1 && bdpt_comm_init_all(ctx.data(), gpus) != BDPT_OK) { MSG("Error: %s", bdpt_last_error(ctx[0])); return 1; }
   BdptStats st0;
   bdpt_get_stats(ctx[0], &st0);
   fprintf(stdout, "[PathTracer] Building BVH from %zu primitives... Done! (%.4f sec)\n", scene.prims.size(), st0.ms_bvh_build / 1e3);
   fprintf(stdout, "[PathTracer] Rendering... "); fflush(stdout);
 
   auto t0 = std::chrono::steady_clock::now();
-  std::vector<int> rcs(gpus, 0);
-  std::vector<std::thread> th;
-  for (int g = 0; g < gpus; g++) {
-    // contiguous blocks of sample indices, remainder to the low ranks (same rule as bdpt/shard.py)
-    int base = ns / gpus, rem = ns % gpus;
-    BdptRenderParams p; memset(&p, 0, sizeof p);
-    p.ns_total = ns; p.max_ray_depth = m; p.n_samples = base + (g < rem ? 1 : 0); p.first_sample = g * base + std::min(g, rem);
-    p.flags = roulette ? BDPT_FLAG_ROULETTE : 0; p.only_t = p.only_s = -1; p.seed = seed;
-    th.emplace_back([&, g, p]() { rcs[g] = bdpt_render(ctx[g], &p); });
+  {
+    std::vector<std::thread> th;
+    for (int g = 0; g < gpus; g++) {
+      // contiguous blocks of sample indices, remainder to the low ranks (same rule as bdpt/shard.py)
+      int base = ns / gpus, rem = ns % gpus;
+      BdptRenderParams p; memset(&p, 0, sizeof p);
+      p.ns_total = ns; p.max_ray_depth = m; p.n_samples = base + (g < rem ? 1 : 0); p.first_sample = g * base + std::min(g, rem);
+      p.flags = (roulette ? BDPT_FLAG_ROULETTE : 0) | (balance ? BDPT_FLAG_BALANCE : 0); p.only_t = p.only_s = -1; p.seed = seed;
+      th.emplace_back([&, g, p]() { rcs[g] = bdpt_render(ctx[g], &p); });
+    }
+    for (auto& t : th) t.join();
   }
-  for (auto& t : th) t.join();
   for (int g = 0; g < gpus; g++) if (rcs[g] != BDPT_OK) { MSG("Error: %s", bdpt_last_error(ctx[g])); return 1; }
-  double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-
-  // one GPU: tone-map on the device; several: add the shards on the host (each is already divided by ns)
+  // several GPUs: ONE ncclReduce of the accumulators to GPU 0 over NVLink, then GPU 0 tone-maps like a single GPU would
+  if (gpus > 1 && bdpt_reduce_all(ctx.data(), gpus, 0) != BDPT_OK) { MSG("Error: %s", bdpt_last_error(ctx[0])); return 1; }
   std::vector<uint8_t> rgba((size_t)W * H * 4);
+  if (bdpt_tonemap_rgba8(ctx[0], BDPT_BUFFER_SUM, rgba.data()) != BDPT_OK) { MSG("Error: %s", bdpt_last_error(ctx[0])); return 1; }
+  double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   unsigned long long rays = 0;
   for (int g = 0; g < gpus; g++) { BdptStats s; bdpt_get_stats(ctx[g], &s); rays += s.rays_closest + s.rays_shadow; }
-  if (gpus == 1) {
-    if (bdpt_tonemap_rgba8(ctx[0], BDPT_BUFFER_SUM, rgba.data()) != BDPT_OK) { MSG("Error: %s", bdpt_last_error(ctx[0])); return 1; }
-  } else {
-    std::vector<float> sum((size_t)W * H * 3, 0.f), part((size_t)W * H * 3);
-    for (int g = 0; g < gpus; g++) {
-      if (bdpt_read_framebuffer(ctx[g], BDPT_BUFFER_SUM, part.data()) != BDPT_OK) { MSG("Error: %s", bdpt_last_error(ctx[g])); return 1; }
-      for (size_t i = 0; i < sum.size(); i++) sum[i] += part[i];
-    }
-    for (int y = 0; y < H; y++)
-      for (int x = 0; x < W; x++) {
-        const float* v = &sum[3 * ((size_t)y * W + x)];
-        uint8_t* o = &rgba[4 * ((size_t)(H - 1 - y) * W + x)];
-        for (int c = 0; c < 3; c++) {  // toColor, util/image.h:194-209
-          float gcol = powf(fmaxf(v[c], 0.f) * 1.41421356f, 1.0f / 2.2f);
-          o[c] = (uint8_t)(fminf(fmaxf(gcol, 0.f), 1.f) * 255.f);
-        }
-        o[3] = 255;
-      }
-  }
   fprintf(stdout, "\r[PathTracer] Rendering... 100%%! (%.4fs)\n", secs);
   fprintf(stdout, "[PathTracer] BVH traced %llu rays.\n", rays);
   fprintf(stdout, "[PathTracer] Average speed %.4f million rays per second.\n", (double)rays / secs * 1e-6);

@@ -46,7 +46,9 @@ enum BdptBuffer {
 
 enum BdptRenderFlags {
   BDPT_FLAG_ROULETTE = 1, /* enable the rule the reference ships commented out (bidirection.cpp:87-93) */
-  BDPT_FLAG_NO_MIS = 2    /* test hook: every strategy weighted 1, the reference's "no MIS" switch (bidirection.cpp:124-126) */
+  BDPT_FLAG_NO_MIS = 2,   /* test hook: every strategy weighted 1, the reference's "no MIS" switch (bidirection.cpp:124-126) */
+  BDPT_FLAG_BALANCE = 4   /* Veach's balance heuristic (exponent 1) instead of the power heuristic with beta = 2 that
+                             multiple_importance_sampling_weight hard-codes (bidirection.cpp:121-293) */
 };
 
 typedef struct BdptRenderParams {
@@ -99,13 +101,30 @@ int bdpt_set_frame(BdptContext* ctx, int width, int height);
 int bdpt_clear(BdptContext* ctx);                               /* BidirectionalPathTracer::clear          */
 int bdpt_render(BdptContext* ctx, const BdptRenderParams* p);   /* accumulates; returns when the GPU is done */
 int bdpt_read_framebuffer(BdptContext* ctx, int which, float* rgb_out); /* D2H, already divided by ns_total  */
-/* Device pointer to the un-normalised fp32 accumulators (eye or light; W*H*3 floats) so that a
- * multi-GPU caller can reduce them in place (ncclReduce / torch.distributed) before reading. */
+/* Device pointer to the un-normalised fp32 accumulators so that a multi-GPU caller can reduce them in place before
+ * reading.  They are ONE allocation of 2*W*H pixels of 4 floats {r, g, b, unused}: the eye image, then the light
+ * image.  which = BDPT_BUFFER_EYE / BDPT_BUFFER_LIGHT: that image (W*H*4 floats); BDPT_BUFFER_SUM: the whole
+ * allocation (2*W*H*4 floats) — what a single ncclReduce / torch.distributed.reduce sums (bdpt_reduce does that). */
 int bdpt_framebuffer_device(BdptContext* ctx, int which, void** device_ptr, size_t* n_floats);
 /* toColor (util/image.h:194-209): exposure sqrt(2), gamma 2.2, clamp, RGBA8, row 0 = TOP as PNGs want
  * (RaytracedRenderer::save_image flips, raytraced_renderer.cpp:690-728). */
 int bdpt_tonemap_rgba8(BdptContext* ctx, int which, uint8_t* rgba_out);
 int bdpt_get_stats(BdptContext* ctx, BdptStats* out);
+
+/* --- multi-GPU: the frame is sharded by sample index (scene replicated, bdpt_render's first_sample / n_samples) and
+ *     ends with ONE sum-reduce of the accumulators to the root over NCCL (NVLink / NVSwitch).  The reference has no
+ *     counterpart (single process; its shared sampleBuffer sits behind one mutex, bidirection.cpp:544-551).
+ *     NCCL is bound at run time (libnccl.so.2); these calls fail with BDPT_ERR_CUDA where it is absent. ------------ */
+#define BDPT_COMM_ID_BYTES 128
+/* One process per GPU: rank 0 makes an id, ships the 128 bytes to the others by any means (torchrun's store, MPI, a
+ * file), then every rank joins.  The reduce runs on the context's stream, ordered after the renders before it. */
+int bdpt_comm_unique_id(void* id_out /* BDPT_COMM_ID_BYTES */);
+int bdpt_comm_init_rank(BdptContext* ctx, int nranks, int rank, const void* id_bytes);
+int bdpt_reduce(BdptContext* ctx, int root);
+/* One process driving n contexts on n devices (pathtracer -g N): ranks are positions in ctxs. */
+int bdpt_comm_init_all(BdptContext** ctxs, int n);
+int bdpt_reduce_all(BdptContext** ctxs, int n, int root);
+int bdpt_comm_destroy(BdptContext* ctx);
 
 /* --- test hooks (parity against the oracle) ------------------------------------------------ */
 /* Host-only (needs no GPU): builds the 8-wide BVH exactly as bdpt_upload_scene does and returns it for

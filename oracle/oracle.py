@@ -43,6 +43,8 @@ def lib():
                      "oracle_light_eval", "oracle_camera_eval"):
             getattr(L, name).argtypes = [C.c_void_p, dp, C.c_long, dp]
             getattr(L, name).restype = None
+        L.oracle_bsdf_sample_ref.argtypes = [C.c_void_p, dp, C.c_long, dp, dp]
+        L.oracle_bsdf_sample_ref.restype = None
         L.oracle_render.restype = C.c_ulonglong
         L.oracle_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_ulonglong, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_int, dp, dp, dp]
@@ -99,19 +101,28 @@ class Oracle:
     def bsdf_sample(self, q):
         return self._batch("oracle_bsdf_sample", q, 7, 7)
 
+    def bsdf_sample_ref(self, q):
+        """sample_f in the reference's own draw order (fresh default-seeded streams).  q: n x {material, wo[3]}.
+        Returns (n x {wi[3], pdf, f[3]}, n x {u1, u2, coin}): the outputs and the uniforms each call drew."""
+        q = np.ascontiguousarray(q, np.float64).reshape(-1, 4)
+        out = np.empty((q.shape[0], 7), np.float64)
+        uni = np.empty((q.shape[0], 3), np.float64)
+        lib().oracle_bsdf_sample_ref(self.h, _dp(q), q.shape[0], _dp(out), _dp(uni))
+        return out, uni
+
     def light_eval(self, q):
         return self._batch("oracle_light_eval", q, 7, 6)
 
     def camera_eval(self, q):
         return self._batch("oracle_camera_eval", q, 5, 11)
 
-    def render(self, ns: int, m: int, *, roulette: int = 0, no_mis: int = 0, rng_mode: int = 1, seed: int = 0, first_sample: int = 0,
+    def render(self, ns: int, m: int, *, roulette: int = 0, no_mis: int = 0, balance: int = 0, rng_mode: int = 1, seed: int = 0, first_sample: int = 0,
                n_samples: int | None = None, threads: int = 1, strategy: tuple[int, int] | None = None):
         """Returns (sum, eye, light) as (H, W, 3) fp64 arrays (row 0 = bottom) and the ray count."""
         n_samples = ns if n_samples is None else n_samples
         bufs = [np.zeros((self.H, self.W, 3), np.float64) for _ in range(3)]
         t, s = strategy if strategy else (-1, -1)
-        rays = lib().oracle_render(self.h, ns, m, (1 if roulette else 0) | (2 if no_mis else 0), rng_mode, seed, first_sample, n_samples, threads, t, s,
+        rays = lib().oracle_render(self.h, ns, m, (1 if roulette else 0) | (2 if no_mis else 0) | (4 if balance else 0), rng_mode, seed, first_sample, n_samples, threads, t, s,
                                    _dp(bufs[0]), _dp(bufs[1]), _dp(bufs[2]))
         return bufs[0], bufs[1], bufs[2], int(rays)
 

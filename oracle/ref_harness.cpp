@@ -16,6 +16,11 @@
 //   bsdf      scene.dae in.bin out.bin
 //       in: N x {material, wo[3], wi[3]} fp64 (7 each); out: N x {f[3], sample_pdf(0,wi),
 //       is_delta, emission[3]} (8 each) via BSDF::f / sample_pdf (bsdf.h:59-127).
+//   bsdf_sample scene.dae in.bin out.bin
+//       in: N x {material, wo[3]} (4 each); out: N x {wi[3], pdf, f[3]} (7 each): BSDF::sample_f called
+//       in order from this fresh process, so the draws are the reference's default-seeded streams
+//       (random_util.h:10-22).  wi and pdf are preset to NaN: RefractionBSDF::sample_f returns
+//       without writing them on total internal reflection (advanced_bsdf.cpp:166-168).
 //   light     scene.dae in.bin out.bin
 //       in: N x {light, p[3], wi[3]} (7 each); out: N x {contain_point, Le[3] (sample_pdf), point_pdf, dir_pdf}
 //   camera    scene.dae W H in.bin out.bin
@@ -247,6 +252,26 @@ int cmd_bsdf(int argc, char** argv) {
   return 0;
 }
 
+int cmd_bsdf_sample(int argc, char** argv) {
+  Loaded L = load_scene(argv[2], 0, 0, 1, 1, 1);
+  std::vector<BSDF*> mats;
+  collect_materials(L.rr->bvh->primitives, mats);
+  std::vector<double> in = read_doubles(argv[3]);
+  size_t n = in.size() / 4;
+  std::vector<double> out(n * 7);
+  for (size_t i = 0; i < n; i++) {
+    const double* q = &in[i * 4];
+    BSDF* b = mats[(size_t)q[0]];
+    Vector3D wi(NAN, NAN, NAN);
+    double pdf = NAN;
+    Vector3D f = b->sample_f(Vector3D(q[1], q[2], q[3]), &wi, &pdf);
+    double* o = &out[i * 7];
+    put3(o, wi); o[3] = pdf; put3(o + 4, f);
+  }
+  write_doubles(argv[4], out);
+  return 0;
+}
+
 int cmd_light(int argc, char** argv) {
   Loaded L = load_scene(argv[2], 0, 0, 1, 1, 1);
   std::vector<double> in = read_doubles(argv[3]);
@@ -353,11 +378,12 @@ int cmd_render(int argc, char** argv) {
 }  // namespace
 
 int main(int argc, char** argv) {
-  if (argc < 2) { fprintf(stderr, "usage: ref_harness dump|intersect|bsdf|light|camera|render ...\n"); return 1; }
+  if (argc < 2) { fprintf(stderr, "usage: ref_harness dump|intersect|bsdf|bsdf_sample|light|camera|render ...\n"); return 1; }
   std::string c = argv[1];
   if (c == "dump" && argc >= 4) return cmd_dump(argc, argv);
   if (c == "intersect" && argc >= 5) return cmd_intersect(argc, argv);
   if (c == "bsdf" && argc >= 5) return cmd_bsdf(argc, argv);
+  if (c == "bsdf_sample" && argc >= 5) return cmd_bsdf_sample(argc, argv);
   if (c == "light" && argc >= 5) return cmd_light(argc, argv);
   if (c == "camera" && argc >= 7) return cmd_camera(argc, argv);
   if (c == "render" && argc >= 9) return cmd_render(argc, argv);

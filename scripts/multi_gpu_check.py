@@ -17,7 +17,8 @@ R.set_stream(torch.cuda.current_stream().cuda_stream)
 R.set_scene(sc); R.set_frame_size(W, H)
 first, n = shard.shard_samples(ns, rank, world)
 R.render(first_sample=first, n_samples=n)
-shard.reduce_to_root(shard.accumulator_tensors(R))
+shard.join_ranks(R, rank, world)
+shard.reduce_frame(R, world)
 torch.cuda.synchronize()
 if rank == 0:
     got = [R.framebuffer(i) for i in range(3)]

@@ -16,6 +16,10 @@ Writes:
   CBspheres_lambertian.strategies.npz   reference per-(t,s) images (debug filter of bidirection.cpp:492-493)
   <name>.converged.npz      reference render at 1024 spp, 64x48, all host threads (statistical pin)
   published_pooled.npz      the author's published 128-spp PNGs (assets/), box-filtered to 60x45
+  <name>.units.npz for CBspheres_microfacet_al_ag / CBspheres_refract (scenes the reference cannot RENDER with
+                            BDPT, but whose BSDF::f, lights, camera and BVH it evaluates fine) and
+  <name>.bsdfsample.npz     BSDF::sample_f of the reference called in order from a fresh process (its own
+                            default-seeded streams): inputs {material, wo}, outputs {wi, pdf, f}   [`extra` mode]
 """
 import os
 import sys
@@ -43,8 +47,11 @@ SCENES = {
 
 
 # scenes the reference cannot render with BDPT (MicrofacetBSDF::sample_pdf aborts, advanced_bsdf.cpp:144-148;
-# RefractionBSDF::sample_f leaves its outputs unset on total internal reflection, :166-168): only the scene dump
+# RefractionBSDF::sample_f leaves its outputs unset on total internal reflection, :166-168): the scene dump, the
+# unit batches (f, lights, camera, rays) and the sample_f replay — everything but a render
 EXTRA_SCENES = ["CBspheres_microfacet_al_ag", "CBspheres_refract"]
+# sample_f replays: every BSDF class the reference has (diffuse, emission, mirror, glass, refraction, microfacet x3)
+SAMPLE_SCENES = ["CBspheres", "CBgems", "CBspheres_microfacet_al_ag", "CBspheres_refract", "CBbunny_microfacet_cu"]
 
 
 def unit(v):
@@ -67,15 +74,78 @@ def ray_batch(sc, rng, n):
     return np.concatenate([r1, r2, r3], 0).astype(np.float32).astype(np.float64)
 
 
+def upper_biased(rng, n):
+    """Unit vectors, two thirds of them in the upper hemisphere (where MicrofacetBSDF is non-zero)."""
+    v = unit(rng.normal(size=(n, 3)))
+    k = 2 * n // 3
+    v[:k, 2] = np.abs(v[:k, 2])
+    return v
+
+
+def extra_units(name, with_scene_units=True):
+    """Unit batches of a scene the reference cannot render, and the sample_f replay."""
+    dae = O.ref_scene(name)
+    tmp = os.path.join(OUT, "scenes", name + ".fscene")
+    O.ref_dump(dae, tmp)
+    sc = fs.load(tmp)
+    os.remove(tmp)
+    rng = np.random.default_rng(sum(map(ord, name)) + 1)
+    M = 900
+    if with_scene_units:
+        sc.save(os.path.join(OUT, "scenes", name + ".fscene.gz"))
+        rays = ray_batch(sc, rng, 3000)
+        hits = O.ref_batch("intersect", dae, rays, 8, 6)
+        bq = np.zeros((M, 7)); bq[:, 0] = rng.integers(0, len(sc.materials), M)
+        bq[:, 1:4] = upper_biased(rng, M); bq[:, 4:7] = upper_biased(rng, M)
+        bq = bq.astype(np.float32).astype(np.float64)
+        bout = O.ref_batch("bsdf", dae, bq, 7, 8)
+        lq = np.zeros((M, 7)); lq[:, 0] = rng.integers(0, len(sc.lights), M)
+        lq[:, 1:4] = rng.uniform([-1, 0, -1], [1, 1.5, 1], (M, 3))
+        on = sc.lights["position"][lq[: M // 2, 0].astype(int)]
+        lq[: M // 2, 2] = on[:, 1]
+        lq[:, 4:7] = unit(rng.normal(size=(M, 3)))
+        lq = lq.astype(np.float32).astype(np.float64)
+        lout = O.ref_batch("light", dae, lq, 7, 6)
+        cq = np.zeros((M, 5)); cq[:, 0:2] = rng.uniform(0, 1, (M, 2)); cq[:, 2:5] = rng.uniform([-1, 0, -1], [1, 1.5, 1], (M, 3))
+        cq = cq.astype(np.float32).astype(np.float64)
+        cout = O.ref_batch("camera", dae, cq, 5, 11, extra=(480, 360))
+        np.savez_compressed(os.path.join(OUT, name + ".units.npz"), rays=rays, hits=hits, bsdf_in=bq, bsdf_out=bout,
+                            light_in=lq, light_out=lout, cam_in=cq, cam_out=cout, cam_wh=np.array([480, 360]))
+    return sc
+
+
+def sample_replay(name):
+    dae = O.ref_scene(name)
+    tmp = os.path.join(OUT, "scenes", name + ".fscene.tmp")
+    O.ref_dump(dae, tmp)
+    sc = fs.load(tmp)
+    os.remove(tmp)
+    rng = np.random.default_rng(sum(map(ord, name)) + 2)
+    M = 1500
+    q = np.zeros((M, 4)); q[:, 0] = rng.integers(0, len(sc.materials), M)
+    q[:, 1:4] = upper_biased(rng, M)
+    q = q.astype(np.float32).astype(np.float64)
+    out = O.ref_batch("bsdf_sample", dae, q, 4, 7)
+    # for the copper bunny only material 0 differs from CBbunny's: f of that one material as well
+    bq = np.zeros((M, 7)); bq[:, 0] = rng.integers(0, len(sc.materials), M)
+    bq[:, 1:4] = upper_biased(rng, M); bq[:, 4:7] = upper_biased(rng, M)
+    bq = bq.astype(np.float32).astype(np.float64)
+    bout = O.ref_batch("bsdf", dae, bq, 7, 8)
+    np.savez_compressed(os.path.join(OUT, name + ".bsdfsample.npz"), samp_in=q, samp_out=out, bsdf_in=bq, bsdf_out=bout,
+                        mat_types=sc.materials["type"].astype(np.int32))
+    print(name, "sample_f replay:", M, "calls;", int(np.isnan(out[:, 3]).sum()), "left unset by the reference (refraction TIR)")
+
+
 def main():
     only = sys.argv[1] if len(sys.argv) > 1 else "all"
     assert O.have_ref(), "build the reference first: make -C oracle ref"
     os.makedirs(os.path.join(OUT, "scenes"), exist_ok=True)
     for name in EXTRA_SCENES:
-        tmp = os.path.join(OUT, "scenes", name + ".fscene")
-        O.ref_dump(O.ref_scene(name), tmp)
-        fs.load(tmp).save(tmp + ".gz")
-        os.remove(tmp)
+        extra_units(name)
+    for name in SAMPLE_SCENES:
+        sample_replay(name)
+    if only == "extra":
+        return
     for name, (W, H, ns, m) in SCENES.items():
         dae = O.ref_scene(name)
         tmp = os.path.join(OUT, "scenes", name + ".fscene")
