@@ -52,10 +52,12 @@ struct BdptContext {
   // batch storage
   size_t cap_B = 0; int cap_m = -1; size_t cap_q = 0;
   char* slab = nullptr;        // backing store of v0..v3, q0..q2, counts
-  size_t slab_bytes = 0, slab_sz_v = 0, slab_sz_q = 0;
+  size_t slab_bytes = 0, slab_sz_v = 0, slab_sz_q = 0, slab_sz_c = 0;
   int slab_align_kb = 2048;    // BDPT_SLAB_ALIGN_KB, tuning only
   float4 *v0 = nullptr, *q0 = nullptr, *q2 = nullptr;
   int* counts = nullptr;
+  uint2* chunks = nullptr;          // the shadow queue's chunk list (kernels.cuh, Job::chunks)
+  size_t cap_chunks = 0;
   char* counters = nullptr;    // 2 MiB block holding qctr and d_stats
   unsigned int* qctr = nullptr;
   unsigned long long* d_stats = nullptr;
@@ -170,6 +172,7 @@ void carve_slab(BdptContext* ctx, char* slab) {
   // shadow queue: 32-byte ray records (q0, stride 2), contributions q2 as a plane
   ctx->q0 = (float4*)(base + 4 * sz_v); ctx->q2 = (float4*)(base + 4 * sz_v + 2 * sz_q);
   ctx->counts = (int*)(base + 4 * sz_v + 3 * sz_q);
+  ctx->chunks = (uint2*)(base + 4 * sz_v + 3 * sz_q + ctx->slab_sz_c);
 }
 
 int ensure_batch_storage(BdptContext* ctx, size_t B, int m, size_t qcap) {
@@ -179,15 +182,18 @@ int ensure_batch_storage(BdptContext* ctx, size_t B, int m, size_t qcap) {
     // apart is what spreads a warp's loads over the HBM channels.)
     const size_t nB = std::max(B, ctx->cap_B); const int nm = std::max(m, ctx->cap_m); const size_t nq = std::max(qcap, ctx->cap_q);
     dfree(ctx->slab);
-    ctx->v0 = nullptr; ctx->q0 = ctx->q2 = nullptr; ctx->counts = nullptr;
+    ctx->v0 = nullptr; ctx->q0 = ctx->q2 = nullptr; ctx->counts = nullptr; ctx->chunks = nullptr;
     ctx->cap_B = 0; ctx->cap_m = -1; ctx->cap_q = 0;   // nothing is held until the allocation below succeeds
     const size_t n = 2 * (size_t)(nm + 1) * nB;
     const size_t align = (size_t)ctx->slab_align_kb << 10;
     auto up = [&](size_t x) { return (x + align - 1) / align * align; };
     const size_t sz_v = up(n * sizeof(float4)), sz_q = up(nq * sizeof(float4)), sz_c = up(2 * nB * sizeof(int));
-    const size_t total = 4 * sz_v + 3 * sz_q + sz_c + align;
+    // chunk list: every block's segment cut into chunks of 256 entries
+    const size_t n_chunks = (nB / BDPT_CONNECT_NT + 1) * ((size_t)BDPT_CONNECT_NT * (nm + 1) * (nm + 1) / 256 + 1);
+    const size_t sz_k = up(n_chunks * sizeof(uint2));
+    const size_t total = 4 * sz_v + 3 * sz_q + sz_c + sz_k + align;
     CK(cudaMalloc(&ctx->slab, total));
-    ctx->slab_bytes = total; ctx->slab_sz_v = sz_v; ctx->slab_sz_q = sz_q;
+    ctx->slab_bytes = total; ctx->slab_sz_v = sz_v; ctx->slab_sz_q = sz_q; ctx->slab_sz_c = sz_c; ctx->cap_chunks = n_chunks;
     carve_slab(ctx, ctx->slab);
     ctx->cap_B = nB; ctx->cap_m = nm; ctx->cap_q = nq;
   }
@@ -216,7 +222,7 @@ void fill_job(BdptContext* ctx, const BdptRenderParams* p, Job* J) {
   memset(J, 0, sizeof(Job));
   J->sc = ctx->sc; J->cam = ctx->cam; J->point_lights = ctx->point_lights;
   J->v0 = ctx->v0; J->counts = ctx->counts;
-  J->q0 = ctx->q0; J->q2 = ctx->q2; J->qctr = ctx->qctr; J->qcap = (unsigned int)ctx->cap_q;
+  J->q0 = ctx->q0; J->q2 = ctx->q2; J->qctr = ctx->qctr; J->chunks = ctx->chunks;
   J->acc_eye = ctx->acc_eye; J->acc_light = ctx->acc_light; J->stats = ctx->d_stats; J->dbg = nullptr;
   // the walk stores a vertex before it tests the depth (bidirection.cpp:82-86): m = 0 behaves as m = 1
   J->seed = p->seed; J->m = std::max(1, p->max_ray_depth); J->first_sample = p->first_sample;
@@ -278,12 +284,16 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
     }
   }
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 1), ctx->stream);
-  // k_connect: the Lambert build needs ~96 registers unspilled and runs best that way; the generic build tolerates
-  // its spills at 80 registers / 6 CTAs per SM (round 1 measurements; BDPT_CONNECT_MINB overrides the bound only)
+  // k_connect at 6 CTAs/SM (80 registers; the Lambert build spills 32 bytes, the generic one ~220): measured on B200
+  // per 2^24 samples — CBbunny 4.00 ms (bounds 4 / 5: 4.24, 8: 6.80, 3: 4.95), CBgems m=16 1.54 (5: 1.63, 8: 2.41),
+  // CBspheres 6.30 (5: 6.60).  BDPT_CONNECT_MINB overrides the bound only, never the trait.
   const unsigned cgrid = (unsigned)((J.B + BDPT_CONNECT_NT - 1) / BDPT_CONNECT_NT);
+  // a sample pushes at most (m+1)^2 shadow rays (t = 1..m+1, s = 1..m+1): a block's segment cannot overflow
+  J.seg_cap = (unsigned)(BDPT_CONNECT_NT * (J.m + 1) * (J.m + 1));
+  J.chunk_cap = (unsigned)std::min<size_t>(ctx->cap_chunks, 0xffffffffu);
   const int ctr = (!TRACE && (ctx->spec & 2)) ? (ctx->traits & (BDPT_TRAIT_LAMBERT | BDPT_TRAIT_NOMF)) : 0;
-  if (ctr & BDPT_TRAIT_LAMBERT) launch_connect<TRACE, BDPT_TRAIT_LAMBERT>(ctx, J, cgrid, ctx->connect_minb ? ctx->connect_minb : 4);
-  else if (ctr & BDPT_TRAIT_NOMF) launch_connect<TRACE, BDPT_TRAIT_NOMF>(ctx, J, cgrid, ctx->connect_minb ? ctx->connect_minb : 5);
+  if (ctr & BDPT_TRAIT_LAMBERT) launch_connect<TRACE, BDPT_TRAIT_LAMBERT>(ctx, J, cgrid, ctx->connect_minb ? ctx->connect_minb : 6);
+  else if (ctr & BDPT_TRAIT_NOMF) launch_connect<TRACE, BDPT_TRAIT_NOMF>(ctx, J, cgrid, ctx->connect_minb ? ctx->connect_minb : 6);
   else launch_connect<TRACE, 0>(ctx, J, cgrid, ctx->connect_minb ? ctx->connect_minb : 6);
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 2), ctx->stream);
   {

@@ -37,11 +37,16 @@ struct Job {
   // vertex records [2*(m+1)][B] x 64 bytes (four float4 per record); counts [2][B] = length | emissive-end << 8
   float4* v0;
   int* counts;
-  // shadow queue: 32-byte ray records {o, tmax | dir, pixel} (q0, stride 2) and the contributions (q2)
+  // shadow queue: 32-byte ray records {o, tmax | dir, pixel} (q0, stride 2) and the contributions (q2), in one
+  // segment of seg_cap entries per k_connect block (qcount[b] of them used): a block appends with a SHARED-memory
+  // counter, so no global atomic sits between a connection and its queue slot
+  // When a block is done it publishes its entries as chunks of <= 256 {first entry, count}: the unit of work of
+  // k_shadow_pt's warps.
   float4 *q0, *q2;
-  // counters: [0] queue entries  [1] shadow cursor  [3] walk cursor (cleared per batch)  [4] queue overflow (per render)
+  uint2* chunks;
+  unsigned int seg_cap, chunk_cap;
+  // counters: [0] chunks published  [1] shadow cursor (chunks)  [3] walk cursor (cleared per batch)  [4] queue overflow (per render)
   unsigned int* qctr;
-  unsigned int qcap;
   // accumulators (un-normalised), W*H float4 each: RGB + one unused lane, so that a splat is ONE 16-byte reduction
   float4 *acc_eye, *acc_light;
   unsigned long long* stats;  // {closest rays, shadow rays, connections}
@@ -274,11 +279,13 @@ __global__ void __launch_bounds__(BDPT_CONNECT_NT, MINB) k_connect(const Job J) 
   __shared__ unsigned s_pix[NT];
   __shared__ int s_smp[NT];
   __shared__ unsigned s_len[NT];       // nE | nL << 8
+  __shared__ unsigned s_qn;            // entries of this block's queue segment
   const DScene& sc = J.sc;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int si0 = blockIdx.x * NT;
   const f3 zero = mk3(0.f);
 
+  if (threadIdx.x == 0) s_qn = 0u;
   // ---- one thread per sample: subpath lengths, pixel, strategy counts
   unsigned cnt[5] = {0u, 0u, 0u, 0u, 0u};
   unsigned nconn = 0;
@@ -355,17 +362,33 @@ __global__ void __launch_bounds__(BDPT_CONNECT_NT, MINB) k_connect(const Job J) 
     f3 ve_pos = zero, ve_n = zero, cdir = zero;
     float woEz = 0.f, woLz = 0.f, cEz = 0.f, cLz = 0.f, hxyE = 0.f, hxyL = 0.f, g = 0.f, dist = 0.f;
     float ls_dir_pdf = 0.f, cam_dir_pdf = 0.f;
-    bool gate = false, in_frame = true;
+    bool gate = false, in_frame = true, push = false;
+    unsigned int target = pix_own;
+
+    // The records this strategy needs are requested TOGETHER, before anything waits for one of them: the eye vertex
+    // (t >= 2), the light vertex (s >= 2) or — for s = 1 — the light subpath's origin, which the MIS chain reads
+    // (SURVEY Q4); then both materials.  (One dependent round trip after the other was a fifth of this kernel's
+    // stall samples: vertex -> its material -> the other vertex -> its material.)
+    const bool needE = valid && t >= 2, needL = valid && s >= 1;
+    float4 ea = make_float4(0.f, 0.f, 0.f, 0.f), eb = ea, ec = ea, ee = ea, la = ea, lb = ea, lc = ea, le = ea;
+    if (needE) { const float4* pe = J.v0 + VSLOT(J, 0, t, sj); ld256(pe, &ea, &eb); ld256(pe + 2, &ec, &ee); }
+    if (needL) { const float4* pl = J.v0 + VSLOT(J, 1, s >= 2 ? s : 1, sj); ld256(pl, &la, &lb); if (s >= 2) ld256(pl + 2, &lc, &le); }
+    E.mat = -1; E.D = 1.f; E.S = 0.f; E.q = 1.f; ME.type = -1; ML.type = -1;
+    if (needE) {
+      E.pos = mk3(ea.x, ea.y, ea.z); E.mat = __float_as_int(ea.w); E.n = mk3(eb.x, eb.y, eb.z); E.D = eb.w;
+      E.alpha = mk3(ec.x, ec.y, ec.z); E.S = ec.w; E.wo = mk3(ee.x, ee.y, ee.z); E.q = ee.w;
+      ME = load_mat<TR>(sc, E.mat);
+    } else {
+      E.pos = J.cam.pos; E.alpha = mk3(1.f); E.n = zero; E.wo = zero;
+    }
+    if (valid && s >= 2) {
+      Lv.pos = mk3(la.x, la.y, la.z); Lv.mat = __float_as_int(la.w); Lv.n = mk3(lb.x, lb.y, lb.z); Lv.D = lb.w;
+      Lv.alpha = mk3(lc.x, lc.y, lc.z); Lv.S = lc.w; Lv.wo = mk3(le.x, le.y, le.z); Lv.q = le.w;
+      ML = load_mat<TR>(sc, Lv.mat);
+    }
 
     if (valid) {
-      E.mat = -1; E.D = 1.f; E.S = 0.f; E.q = 1.f; ME.type = -1;
-      if (t >= 2) {
-        E = load_vtx(J, 0, t, sj);
-        ME = load_mat<TR>(sc, E.mat);
-        woEz = dot(E.n, E.wo);   // local z of the direction back along the eye subpath
-      } else {
-        E.pos = J.cam.pos; E.alpha = mk3(1.f); E.n = zero; E.wo = zero;
-      }
+      if (t >= 2) woEz = dot(E.n, E.wo);   // local z of the direction back along the eye subpath
       if (s == 0) {
         // c_{0,t}: the eye subpath hit an emitter (bidirection.cpp:307-328)
         f3 c = (t >= 2 && ME.type == BDPT_MAT_EMISSION) ? ME.radiance : zero;
@@ -415,10 +438,7 @@ __global__ void __launch_bounds__(BDPT_CONNECT_NT, MINB) k_connect(const Job J) 
           pA /= (float)sc.n_lights;
           Lv.alpha = rad * (1.0f / pA);
           Lv.mat = -1; Lv.q = 1.f; Lv.D = pA; Lv.S = 1.f; Lv.wo = zero;
-          ML.type = -1;
         } else {
-          Lv = load_vtx(J, 1, s, sj);
-          ML = load_mat<TR>(sc, Lv.mat);
           woLz = dot(Lv.n, Lv.wo);
         }
         // ---- eye-side endpoint ve (t == 1: the pinhole, bidirection.cpp:360-383)
@@ -429,7 +449,7 @@ __global__ void __launch_bounds__(BDPT_CONNECT_NT, MINB) k_connect(const Job J) 
           float We = camera_sample_ray_pdf(J.cam, Lv.pos, &wi, &dd, &cam_dir_pdf, &eye_x, &eye_y);
           ve_n = -wi;
           eye_alpha = mk3(We);
-          // the raster position is known here: a connection that leaves the frame never reaches the queue
+          // a connection that leaves the frame never reaches the queue
           in_frame = eye_x >= 0 && eye_y >= 0 && eye_x < J.cam.W && eye_y < J.cam.H;
         }
         const f3 cv = Lv.pos - ve_pos;
@@ -452,15 +472,6 @@ __global__ void __launch_bounds__(BDPT_CONNECT_NT, MINB) k_connect(const Job J) 
         gate = norm(contrib) > BDPT_EPS_F;   // bidirection.cpp:445
       }
     }
-    // The queue slot is reserved here, before the weight is known: the atomic's round trip to L2 then overlaps the
-    // weight computation.  A connection that passes the gate but ends up with no weight (0 / NaN: rare) fills its
-    // slot with a null ray.  Every lane of the warp is here (the round loop is uniform), so the votes are full-mask.
-    const bool reserve = !TRACE && gate && in_frame;
-    const unsigned r_mask = __ballot_sync(0xffffffffu, reserve);
-    unsigned r_ticket = 0u;
-    if (r_mask != 0u && lane == __ffs(r_mask) - 1) r_ticket = atomicAdd(J.qctr + 0, (unsigned int)__popc(r_mask));
-    bool push = false;
-    unsigned int target = pix_own;
     if (gate && (TRACE || in_frame)) {   // (the trace hook records the weight of off-frame connections too)
       // ---- MIS weight (bidirection.cpp:121-293 in closed form, see header)
       double winv = 1.0;
@@ -492,28 +503,23 @@ __global__ void __launch_bounds__(BDPT_CONNECT_NT, MINB) k_connect(const Job J) 
         }
         winv += (double)mis_pow(J, r_s) * (double)S_s;
       } else {
-        // s == 1: the chain is evaluated at the ORIGINAL light-subpath origin
-        float4 a, b;   // light_path[1]
-        ld256(J.v0 + VSLOT(J, 1, 1, sj), &a, &b);
-        f3 wv = mk3(a.x, a.y, a.z) - ve_pos;
+        // s == 1: the chain is evaluated at the ORIGINAL light-subpath origin: light_path[1] = {la, lb}
+        f3 wv = mk3(la.x, la.y, la.z) - ve_pos;
         float d2 = dot(wv, wv);
         f3 wd = wv * rsqrtf(d2);
         const float cosA = dot(ve_n, wd);
         float hx = 0.f;
         if (!(TR & BDPT_TRAIT_NOMF) && !(TR & BDPT_TRAIT_LAMBERT) && ME.type == BDPT_MAT_MICROFACET) hx = half_xy2_world(E.wo, wd, E.n);
         const float P_el = t == 1 ? cam_dir_pdf : bsdf_pdf_mis_z(ME, woEz, cosA, hx) * E.q;
-        float gp = fabsf(cosA * dot(wd, mk3(b.x, b.y, b.z))) / d2;
-        float r_s = P_el * gp / b.w;
+        float gp = fabsf(cosA * dot(wd, mk3(lb.x, lb.y, lb.z))) / d2;
+        float r_s = P_el * gp / lb.w;
         winv += (double)mis_pow(J, r_s);
       }
       w = J.no_mis ? 1.f : (float)(1.0 / winv);
       if (!(w >= 0.f)) w = 0.f;  // NaN guard
       ill = contrib * w;
-      push = w > 0.f;
-      if (t == 1) {
-        if (in_frame) target = (unsigned int)(eye_y * J.cam.W + eye_x) | 0x80000000u;
-        else push = false;
-      }
+      push = w > 0.f && in_frame;
+      if (t == 1 && in_frame) target = (unsigned int)(eye_y * J.cam.W + eye_x) | 0x80000000u;
     }
     if (TRACE) {
       if (valid && s > 0) {
@@ -526,23 +532,37 @@ __global__ void __launch_bounds__(BDPT_CONNECT_NT, MINB) k_connect(const Job J) 
         rr[0] = t; rr[1] = s; rr[2] = contrib.x; rr[3] = contrib.y; rr[4] = contrib.z; rr[5] = w; rr[6] = eye_x; rr[7] = eye_y;
       }
     }
-    // ---- append {ray, pixel, weighted contribution} to the shadow queue
-    const unsigned a_mask = TRACE ? __ballot_sync(0xffffffffu, push) : r_mask;
+    // ---- append {ray, pixel, weighted contribution} to this block's segment of the shadow queue: one shared-memory
+    // atomic per warp (every lane of the warp is here — the round loop is uniform — so the votes are full-mask)
+    const unsigned a_mask = __ballot_sync(0xffffffffu, push);
     if (a_mask != 0u) {
       const int leader = __ffs(a_mask) - 1;
-      if (TRACE && lane == leader) r_ticket = atomicAdd(J.qctr + 0, (unsigned int)__popc(a_mask));
-      const unsigned slot0 = __shfl_sync(0xffffffffu, r_ticket, leader);
-      if (TRACE ? push : reserve) {
-        const unsigned idx = slot0 + __popc(a_mask & ((1u << lane) - 1u));
-        if (idx >= J.qcap) J.qctr[4] = 1u;
+      unsigned ticket = 0u;
+      if (lane == leader) ticket = atomicAdd(&s_qn, (unsigned int)__popc(a_mask));
+      const unsigned slot0 = __shfl_sync(0xffffffffu, ticket, leader);
+      if (push) {
+        const unsigned k_in = slot0 + __popc(a_mask & ((1u << lane) - 1u));
+        if (k_in >= J.seg_cap) J.qctr[4] = 1u;
         else {
-          const float tmax = push ? dist - BDPT_EPS_F : -1.f;     // null ray: nothing to trace, adds zero
-          const f3 add = push ? ill : zero;
-          st256(J.q0 + 2 * (size_t)idx, make_float4(ve_pos.x, ve_pos.y, ve_pos.z, tmax),
-                make_float4(cdir.x, cdir.y, cdir.z, __uint_as_float(push ? target : pix_own)));
-          J.q2[idx] = make_float4(add.x, add.y, add.z, 0.f);
+          const size_t idx = (size_t)blockIdx.x * J.seg_cap + k_in;
+          st256(J.q0 + 2 * idx, make_float4(ve_pos.x, ve_pos.y, ve_pos.z, dist - BDPT_EPS_F),
+                make_float4(cdir.x, cdir.y, cdir.z, __uint_as_float(target)));
+          J.q2[idx] = make_float4(ill.x, ill.y, ill.z, 0.f);
         }
       }
+    }
+  }
+  __syncthreads();
+  {
+    // publish the segment as chunks of 256 entries: one global atomic per block
+    const unsigned n = min(s_qn, J.seg_cap), nchunks = (n + 255u) >> 8;
+    __shared__ unsigned s_c0;
+    if (threadIdx.x == 0 && nchunks) s_c0 = atomicAdd(J.qctr + 0, nchunks);
+    __syncthreads();
+    for (unsigned c = threadIdx.x; c < nchunks; c += NT) {
+      const unsigned slot = s_c0 + c;
+      if (slot < J.chunk_cap) J.chunks[slot] = make_uint2(blockIdx.x * J.seg_cap + (c << 8), min(256u, n - (c << 8)));
+      else J.qctr[4] = 1u;
     }
   }
   const unsigned tc = __reduce_add_sync(0xffffffffu, nconn);
@@ -607,6 +627,27 @@ __device__ inline unsigned warp_fetch(unsigned* cursor, unsigned total, unsigned
   return got ? my : BDPT_NONE;
 }
 
+// The shadow queue is a list of chunks of <= 256 entries (Job::chunks, published by k_connect's blocks): a warp takes a
+// chunk with one atomic and hands its entries to idle lanes as above.
+__device__ inline unsigned warp_fetch_chunk(const Job& J, unsigned nchunks, bool want, WarpFetch& wf) {
+  const unsigned mask = __ballot_sync(0xffffffffu, want);
+  if (mask == 0u || wf.exhausted) return BDPT_NONE;
+  const int lane = threadIdx.x & 31;
+  if (wf.next >= wf.end) {
+    unsigned c = 0;
+    if (lane == 0) c = atomicAdd(J.qctr + 1, 1u);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    if (c >= nchunks) { wf.exhausted = true; return BDPT_NONE; }
+    const uint2 d = __ldg(J.chunks + c);
+    wf.next = d.x;
+    wf.end = d.x + d.y;
+  }
+  const unsigned my = wf.next + __popc(mask & ((1u << lane) - 1u));
+  const bool got = want && my < wf.end;
+  wf.next = min(wf.next + (unsigned)__popc(mask), wf.end);
+  return got ? my : BDPT_NONE;
+}
+
 // Copies the first `ntop` BVH nodes (the upper levels: nodes are stored breadth first) into shared memory.
 __device__ inline void stage_top_nodes(const Job& J, uint4* top) {
   for (int i = threadIdx.x; i < J.ntop * 5; i += blockDim.x) top[i] = J.sc.nodes[i];
@@ -619,7 +660,7 @@ template <int MINB, int TR = 0, int FETCH = 12, int SPLAT = 16>
 __global__ void __launch_bounds__(128, MINB) k_shadow_pt(const Job J) {
   extern __shared__ uint4 top[];
   stage_top_nodes(J, top);
-  const unsigned n = min(J.qctr[0], J.qcap);
+  const unsigned nchunks = min(J.qctr[0], J.chunk_cap);
   Trav T;
   uint2 stack[BDPT_STACK];
   bool active = false;
@@ -636,13 +677,11 @@ __global__ void __launch_bounds__(128, MINB) k_shadow_pt(const Job J) {
       if (pend != BDPT_NONE) { shadow_splat(J, parked, pend); pend = BDPT_NONE; }
     }
     if (!wf.exhausted && (__popc(idle) >= FETCH || idle == 0xffffffffu)) {
-      unsigned my = warp_fetch(J.qctr + 1, n, 256u, !active, wf);
+      unsigned my = warp_fetch_chunk(J, nchunks, !active, wf);
       if (my != BDPT_NONE) {
         float4 a, b; ld256(J.q0 + 2 * (size_t)my, &a, &b);
-        if (a.w >= 0.f) {   // tmax < 0: a reserved slot whose connection turned out to carry nothing
-          T.begin(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), BDPT_EPS_F, a.w);
-          idx = my; active = true;
-        }
+        T.begin(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), BDPT_EPS_F, a.w);
+        idx = my; active = true;
       }
     }
     if (__ballot_sync(0xffffffffu, active) == 0u) {
