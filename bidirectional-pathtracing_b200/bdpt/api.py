@@ -53,7 +53,7 @@ EXPORTS = ["bdpt_create", "bdpt_destroy", "bdpt_last_error", "bdpt_set_stream", 
            "bdpt_set_camera", "bdpt_set_frame", "bdpt_clear", "bdpt_render", "bdpt_read_framebuffer",
            "bdpt_framebuffer_device", "bdpt_tonemap_rgba8", "bdpt_get_stats", "bdpt_intersect_batch",
            "bdpt_occluded_batch", "bdpt_bsdf_eval_batch", "bdpt_bsdf_sample_batch", "bdpt_light_eval_batch",
-           "bdpt_camera_eval_batch", "bdpt_trace_sample", "bdpt_host_build_bvh",
+           "bdpt_camera_eval_batch", "bdpt_trace_sample", "bdpt_host_build_bvh", "bdpt_device_bvh",
            "bdpt_comm_unique_id", "bdpt_comm_init_rank", "bdpt_comm_init_all", "bdpt_reduce", "bdpt_reduce_all",
            "bdpt_comm_destroy"]
 
@@ -89,6 +89,8 @@ def load_library():
     L.bdpt_occluded_batch.argtypes = [vp, dp, C.c_size_t, C.POINTER(C.c_int32)]
     L.bdpt_trace_sample.argtypes = [vp, C.POINTER(RenderParams), C.c_int, C.c_int, C.c_int, dp, C.c_size_t,
                                     C.POINTER(C.c_size_t)]
+    L.bdpt_device_bvh.argtypes = [vp, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                  C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.bdpt_comm_unique_id.argtypes = [vp]
     L.bdpt_comm_init_rank.argtypes = [vp, C.c_int, C.c_int, vp]
     L.bdpt_comm_init_all.argtypes = [C.POINTER(vp), C.c_int]
@@ -217,6 +219,17 @@ class Renderer:
         return s.asdict()
 
     # -- test hooks
+    def device_bvh(self):
+        """(nodes (n,20) uint32, prim_order, depth, PLOC rounds) of the tree the device built for the current scene."""
+        u32p = C.POINTER(C.c_uint32)
+        nn, depth, rounds = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self._ck(self.L.bdpt_device_bvh(self.h, None, 0, C.byref(nn), None, C.byref(depth), C.byref(rounds)))
+        nodes = np.zeros((nn.value, 20), np.uint32)
+        order = np.zeros(len(self._keep[3]), np.uint32)
+        self._ck(self.L.bdpt_device_bvh(self.h, nodes.ctypes.data_as(u32p), nn.value, C.byref(nn), order.ctypes.data_as(u32p),
+                                        C.byref(depth), C.byref(rounds)))
+        return nodes, order, depth.value, rounds.value
+
     def _batch(self, fn, arr, n_in, n_out):
         arr = np.ascontiguousarray(arr, np.float64).reshape(-1, n_in)
         out = np.empty((arr.shape[0], n_out), np.float64)

@@ -13,6 +13,7 @@
 
 #include "../../include/bdpt_b200.h"
 #include "bvh8.h"
+#include "bvh_gpu.cuh"
 #include "kernels.cuh"
 
 using namespace bdpt;
@@ -37,6 +38,12 @@ struct BdptContext {
   size_t cap_scene[6] = {0, 0, 0, 0, 0, 0};
   uint32_t bvh_nodes = 0, bvh_depth = 0;
   double ms_bvh_build = 0;
+  // device build (bvh_gpu.cuh): workspace (grow-only), pinned counters, the leaf order it produced
+  char* bvh_ws = nullptr; size_t bvh_ws_bytes = 0;
+  unsigned int* h_bvh = nullptr;
+  uint32_t* d_prim_order = nullptr;     // points into bvh_ws
+  int bvh_on_device = 1;                // BDPT_BVH=host builds on the host instead (bvh8.cpp: the checker)
+  uint32_t bvh_rounds = 0;              // PLOC rounds of the last device build
 
   // frame
   int W = 0, H = 0;
@@ -341,6 +348,117 @@ int run_hook(BdptContext* ctx, const double* in, size_t n, int n_in, double* out
   return BDPT_OK;
 }
 
+
+// ---- device build of the wide BVH and of the leaf-ordered scene records (bvh_gpu.cuh).  On return the scene arrays
+// d_nodes / d_prims / d_shading / d_prims64 are filled (stream-ordered) and *n_nodes / *depth are known.
+int ensure_dev(void** p, size_t* cap, size_t bytes) {
+  if (bytes <= *cap && *p) return 0;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *cap = 0;
+  if (cudaMalloc(p, bytes) != cudaSuccess) return 1;
+  *cap = bytes;
+  return 0;
+}
+
+int build_scene_on_device(BdptContext* ctx, const BdptPrim* prims, uint32_t n_prims, uint32_t* n_nodes, uint32_t* depth) {
+  const int N = (int)n_prims;
+  const size_t n2 = 2 * (size_t)N;
+  cudaStream_t st = ctx->stream;
+  // scene arrays (grow-only)
+  if (ensure_dev((void**)&ctx->d_nodes, &ctx->cap_scene[0], (size_t)N * 80) || ensure_dev((void**)&ctx->d_prims, &ctx->cap_scene[1], 3 * (size_t)N * sizeof(float4)) ||
+      ensure_dev((void**)&ctx->d_shading, &ctx->cap_scene[2], 3 * (size_t)N * sizeof(float4)) || ensure_dev((void**)&ctx->d_prims64, &ctx->cap_scene[5], 10 * (size_t)N * sizeof(double)))
+    return fail(ctx, BDPT_ERR_CUDA, "cudaMalloc (scene arrays)");
+  // workspace
+  size_t sort_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, N, 0, 63, st);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_raw = take((size_t)N * sizeof(BdptPrim)), o_blo = take(N * sizeof(float4)), o_bhi = take(N * sizeof(float4));
+  const size_t o_k0 = take(N * 8), o_k1 = take(N * 8), o_v0 = take(N * 4), o_v1 = take(N * 4), o_sort = take(sort_bytes);
+  const size_t o_tlo = take(n2 * sizeof(float4)), o_thi = take(n2 * sizeof(float4)), o_l = take(n2 * 4), o_r = take(n2 * 4), o_p = take(n2 * 4), o_c = take(n2 * 4), o_lp = take(N * 4);
+  const size_t o_cl = take(N * 4), o_clo = take(N * sizeof(float4)), o_chi = take(N * sizeof(float4)), o_nn = take(N * 4);
+  const size_t o_oid = take(N * 4), o_olo = take(N * sizeof(float4)), o_ohi = take(N * sizeof(float4)), o_keep = take(N);
+  const size_t nb = (size_t)(N + BDPT_PLOC_BLOCK - 1) / BDPT_PLOC_BLOCK;
+  const size_t o_bc = take(nb * 4), o_bo = take(nb * 4), o_ctr = take(64);
+  const size_t o_C = take(n2 * 8 * sizeof(float)), o_split = take(n2 * 9), o_leaf = take(n2), o_visit = take(n2 * 4);
+  const size_t o_it0 = take((size_t)N * sizeof(int2)), o_it1 = take((size_t)N * sizeof(int2)), o_po = take(N * 4);
+  if (ensure_dev((void**)&ctx->bvh_ws, &ctx->bvh_ws_bytes, off)) return fail(ctx, BDPT_ERR_CUDA, "cudaMalloc (BVH build workspace)");
+  char* W = ctx->bvh_ws;
+  BdptPrim* d_raw = (BdptPrim*)(W + o_raw);
+  float4 *blo = (float4*)(W + o_blo), *bhi = (float4*)(W + o_bhi);
+  unsigned long long *k0 = (unsigned long long*)(W + o_k0), *k1 = (unsigned long long*)(W + o_k1);
+  uint32_t *v0 = (uint32_t*)(W + o_v0), *v1 = (uint32_t*)(W + o_v1);
+  DevTree T{(float4*)(W + o_tlo), (float4*)(W + o_thi), (int*)(W + o_l), (int*)(W + o_r), (int*)(W + o_p), (int*)(W + o_c), (uint32_t*)(W + o_lp)};
+  int* cluster = (int*)(W + o_cl); float4 *clo = (float4*)(W + o_clo), *chi = (float4*)(W + o_chi); int* nn = (int*)(W + o_nn);
+  int* out_id = (int*)(W + o_oid); float4 *olo = (float4*)(W + o_olo), *ohi = (float4*)(W + o_ohi); unsigned char* keep = (unsigned char*)(W + o_keep);
+  unsigned *bcount = (unsigned*)(W + o_bc), *boff = (unsigned*)(W + o_bo), *ctr = (unsigned*)(W + o_ctr);
+  float* C = (float*)(W + o_C); uint8_t *split = (uint8_t*)(W + o_split), *is_leaf = (uint8_t*)(W + o_leaf); unsigned* visit = (unsigned*)(W + o_visit);
+  int2* items[2] = {(int2*)(W + o_it0), (int2*)(W + o_it1)};
+  uint32_t* prim_order = (uint32_t*)(W + o_po);
+  ctx->d_prim_order = prim_order;
+  unsigned* cb = ctr + 8;      // centroid bounds, 6 encoded words
+  unsigned* ectr = ctr + 4;    // emission counters
+
+  const int TB = 256, G = (N + TB - 1) / TB;
+  CK(cudaMemcpyAsync(d_raw, prims, (size_t)N * sizeof(BdptPrim), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(cb, 0xff, 3 * sizeof(unsigned), st));
+  CK(cudaMemsetAsync(cb + 3, 0, 3 * sizeof(unsigned), st));
+  k_bvh_bounds<<<G, TB, 0, st>>>(d_raw, N, blo, bhi, cb);
+  k_bvh_morton<<<G, TB, 0, st>>>(blo, bhi, N, cb, k0, v0);
+  cub::DeviceRadixSort::SortPairs(W + o_sort, sort_bytes, (const unsigned long long*)k0, k1, (const uint32_t*)v0, v1, N, 0, 63, st);
+  k_bvh_leaves<<<G, TB, 0, st>>>(blo, bhi, v1, N, T, cluster, clo, chi);
+  ctx->stats.kernel_launches += 4;
+  ctx->h_bvh[0] = (unsigned)N; ctx->h_bvh[1] = (unsigned)N; ctx->h_bvh[2] = (unsigned)N; ctx->h_bvh[3] = 0;
+  CK(cudaMemcpyAsync(ctr, ctx->h_bvh, 4 * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+  // PLOC rounds; the cluster count comes back every few rounds (the kernels of a finished build are no-ops)
+  int n_upper = N; uint32_t rounds = 0;
+  while (n_upper > 1) {
+    for (int r = 0; r < 4; r++) {
+      const int g = (n_upper + BDPT_PLOC_BLOCK - 1) / BDPT_PLOC_BLOCK;
+      k_ploc_nearest<<<g, BDPT_PLOC_BLOCK, 0, st>>>(ctr, clo, chi, nn);
+      k_ploc_merge<<<g, BDPT_PLOC_BLOCK, 0, st>>>(ctr, nn, cluster, clo, chi, T, out_id, olo, ohi, keep, bcount);
+      k_ploc_scan<<<1, 1024, 0, st>>>(ctr, bcount, boff);
+      k_ploc_scatter<<<g, BDPT_PLOC_BLOCK, 0, st>>>(ctr, keep, boff, out_id, olo, ohi, cluster, clo, chi);
+      k_ploc_advance<<<1, 1, 0, st>>>(ctr);
+      ctx->stats.kernel_launches += 5; rounds++;
+    }
+    CK(cudaMemcpyAsync(ctx->h_bvh + 8, ctr, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int n_now = (int)ctx->h_bvh[8];
+    if (n_now < 1 || n_now > n_upper) return fail(ctx, BDPT_ERR_CUDA, "device BVH build: cluster count went wrong");
+    if (n_now == n_upper && n_now > 1 && rounds > 4096) return fail(ctx, BDPT_ERR_CUDA, "device BVH build does not converge");
+    n_upper = n_now;
+  }
+  ctx->bvh_rounds = rounds;
+  // collapse DP, bottom-up
+  CK(cudaMemsetAsync(visit, 0, n2 * 4, st));
+  WideParams P; P.max_leaf = 3; P.prim_cost = 0.8f;
+  if (const char* e = getenv("BDPT_BVH_LEAF")) P.max_leaf = std::max(1, std::min(3, atoi(e)));
+  if (const char* e = getenv("BDPT_BVH_CP")) P.prim_cost = (float)atof(e);
+  k_bvh_collapse_dp<<<G, TB, 0, st>>>(T, N, P, C, split, is_leaf, visit);
+  // wide nodes, one level per launch (items of level 0: {node 0, root = the last cluster})
+  k_bvh_root<<<1, 1, 0, st>>>(cluster, items[0], ectr);
+  ctx->stats.kernel_launches += 2;
+  uint32_t n_items = 1, levels = 0; int cur = 0;
+  while (n_items > 0) {
+    if (levels >= BDPT_STACK) return fail(ctx, BDPT_ERR_SCENE, "BVH deeper than the traversal stack");
+    k_bvh_emit_level<<<(n_items + 63) / 64, 64, 0, st>>>(T, split, is_leaf, items[cur], (int)n_items, (uint32_t*)ctx->d_nodes, prim_order, items[cur ^ 1], ectr);
+    ctx->stats.kernel_launches += 1; levels++;
+    CK(cudaMemcpyAsync(ctx->h_bvh + 8, ectr, 3 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemsetAsync(ectr + 2, 0, sizeof(unsigned), st));
+    CK(cudaStreamSynchronize(st));
+    n_items = ctx->h_bvh[10];
+    if (ctx->h_bvh[8] > (unsigned)N || n_items > (unsigned)N) return fail(ctx, BDPT_ERR_CUDA, "device BVH build: node count went wrong");
+    cur ^= 1;
+  }
+  if (ctx->h_bvh[9] != (unsigned)N) return fail(ctx, BDPT_ERR_CUDA, "device BVH build: not every primitive reached a leaf");
+  *n_nodes = ctx->h_bvh[8]; *depth = levels;
+  k_bvh_records<<<G, TB, 0, st>>>(d_raw, prim_order, N, ctx->d_prims, ctx->d_shading, ctx->d_prims64);
+  ctx->stats.kernel_launches += 1;
+  CK(cudaGetLastError());
+  return BDPT_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -375,6 +493,8 @@ int bdpt_create(int device, BdptContext** out) {
   if (const char* e = getenv("BDPT_VARIANT")) ctx->variant = atoi(e);
   if (const char* e = getenv("BDPT_WALK_CTAS")) ctx->walk_ctas = std::max(1, atoi(e));
   if (const char* e = getenv("BDPT_SHADOW_CTAS")) ctx->shadow_ctas = std::max(1, atoi(e));
+  if (const char* e = getenv("BDPT_BVH")) ctx->bvh_on_device = strcmp(e, "host") != 0;
+  if (cudaMallocHost(&ctx->h_bvh, 16 * sizeof(unsigned int)) != cudaSuccess) { g_create_error = "cudaMallocHost failed"; cudaStreamDestroy(ctx->stream); delete ctx; return BDPT_ERR_CUDA; }
   *out = ctx;
   return BDPT_OK;
 }
@@ -388,6 +508,8 @@ void bdpt_destroy(BdptContext* ctx) {
   dfree(ctx->acc); dfree(ctx->resolve_tmp); dfree(ctx->rgba_tmp);
   dfree(ctx->slab); dfree(ctx->counters); ctx->qctr = nullptr; ctx->d_stats = nullptr;
   if (ctx->h_qctr) cudaFreeHost(ctx->h_qctr);
+  if (ctx->h_bvh) cudaFreeHost(ctx->h_bvh);
+  dfree(ctx->bvh_ws);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -422,38 +544,16 @@ int bdpt_upload_scene(BdptContext* ctx, const BdptCamera* camera, const BdptMate
   }
 
   auto t0 = std::chrono::steady_clock::now();
-  std::vector<BuildPrim> bp;
-  make_build_prims(prims, n_prims, &bp);
-  Bvh8 bvh;
-  build_bvh8(bp, &bvh);
-  ctx->ms_bvh_build = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-  if (bvh.max_depth >= BDPT_STACK) return fail(ctx, BDPT_ERR_SCENE, "BVH deeper than the traversal stack");
-
-  // leaf-ordered primitive + shading records
-  std::vector<float4> hp(3 * (size_t)std::max<uint32_t>(n_prims, 1)), hs(3 * (size_t)std::max<uint32_t>(n_prims, 1));
-  std::vector<double> h64(10 * (size_t)std::max<uint32_t>(n_prims, 1), 0.0);
-  for (size_t k = 0; k < bvh.prim_order.size(); k++) {
-    uint32_t id = bvh.prim_order[k];
-    const BdptPrim& p = prims[id];
-    const double* d = p.data;
-    for (int a = 0; a < 9; a++) h64[10 * k + a] = d[a];  // triangle p1 p2 p3 / sphere centre, radius
-    if (p.type == BDPT_PRIM_TRIANGLE) {
-      float v0[3], v1[3], v2[3];
-      for (int a = 0; a < 3; a++) { v0[a] = (float)d[a]; v1[a] = (float)d[3 + a]; v2[a] = (float)d[6 + a]; }
-      hp[3 * k + 0] = make_float4(v0[0], v0[1], v0[2], ibits((int)id));
-      hp[3 * k + 1] = make_float4(v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2], ibits(p.material));
-      hp[3 * k + 2] = make_float4(v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2], 0.f);
-      hs[3 * k + 0] = make_float4((float)d[9], (float)d[10], (float)d[11], 0.f);
-      hs[3 * k + 1] = make_float4((float)d[12], (float)d[13], (float)d[14], 0.f);
-      hs[3 * k + 2] = make_float4((float)d[15], (float)d[16], (float)d[17], 0.f);
-    } else {
-      float r = (float)d[3];
-      hp[3 * k + 0] = make_float4((float)d[0], (float)d[1], (float)d[2], ibits((int)id));
-      hp[3 * k + 1] = make_float4(r, (float)(d[3] * d[3]), 0.f, ibits(p.material | (int)0x80000000));
-      hp[3 * k + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
-      hs[3 * k + 0] = hs[3 * k + 1] = hs[3 * k + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  // grow-only device storage: re-uploading a scene of the same size allocates nothing
+  auto ensure = [&](void** p, size_t* cap, size_t bytes) -> cudaError_t {
+    if (bytes <= *cap && *p) return cudaSuccess;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaSuccess) *cap = bytes;
+    return e;
+  };
   std::vector<float4> hm(5 * (size_t)std::max<uint32_t>(n_materials, 1));
   for (uint32_t i = 0; i < n_materials; i++) {
     const BdptMaterial& m = materials[i];
@@ -474,37 +574,74 @@ int bdpt_upload_scene(BdptContext* ctx, const BdptCamera* camera, const BdptMate
     hl[5 * i + 3] = make_float4((float)l.dim_x[0], (float)l.dim_x[1], (float)l.dim_x[2], 0.f);
     hl[5 * i + 4] = make_float4((float)l.dim_y[0], (float)l.dim_y[1], (float)l.dim_y[2], 0.f);
   }
-
-  CK(cudaStreamSynchronize(ctx->stream));
-  // grow-only device storage: re-uploading a scene of the same size allocates nothing
-  auto ensure = [&](void** p, size_t* cap, size_t bytes) -> cudaError_t {
-    if (bytes <= *cap && *p) return cudaSuccess;
-    if (*p) cudaFree(*p);
-    *p = nullptr; *cap = 0;
-    cudaError_t e = cudaMalloc(p, bytes);
-    if (e == cudaSuccess) *cap = bytes;
-    return e;
-  };
-  CK(ensure((void**)&ctx->d_nodes, &ctx->cap_scene[0], bvh.nodes.size() * sizeof(uint32_t)));
-  CK(ensure((void**)&ctx->d_prims, &ctx->cap_scene[1], hp.size() * sizeof(float4)));
-  CK(ensure((void**)&ctx->d_shading, &ctx->cap_scene[2], hs.size() * sizeof(float4)));
   CK(ensure((void**)&ctx->d_mats, &ctx->cap_scene[3], hm.size() * sizeof(float4)));
   CK(ensure((void**)&ctx->d_lights, &ctx->cap_scene[4], hl.size() * sizeof(float4)));
-  CK(ensure((void**)&ctx->d_prims64, &ctx->cap_scene[5], h64.size() * sizeof(double)));
-  CK(cudaMemcpyAsync(ctx->d_prims64, h64.data(), h64.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->d_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->d_prims, hp.data(), hp.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->d_shading, hs.data(), hs.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_mats, hm.data(), hm.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_lights, hl.data(), hl.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+
+  uint32_t n_nodes = 0, depth = 0;
+  if (ctx->bvh_on_device && n_prims >= 1) {
+    // the raw primitives go up as they are; bounds, Morton order, PLOC, the 8-wide collapse and the leaf-ordered
+    // records are all made on the device (bvh_gpu.cuh) — what BVHAccel::construct_bvh does on one host thread
+    int rc = build_scene_on_device(ctx, prims, n_prims, &n_nodes, &depth);
+    if (rc) return rc;
+  } else {
+    // BDPT_BVH=host (and the empty scene): binned-SAH build on the host (bvh8.cpp), kept as the checker
+    std::vector<BuildPrim> bp;
+    make_build_prims(prims, n_prims, &bp);
+    Bvh8 bvh;
+    {
+      const char* algo = getenv("BDPT_BVH_HOST_ALGO");
+      if (algo && !strcmp(algo, "ploc")) build_bvh8_ploc(bp, &bvh); else build_bvh8(bp, &bvh);
+    }
+    if (bvh.max_depth >= BDPT_STACK) return fail(ctx, BDPT_ERR_SCENE, "BVH deeper than the traversal stack");
+    // leaf-ordered primitive + shading records
+    std::vector<float4> hp(3 * (size_t)std::max<uint32_t>(n_prims, 1)), hs(3 * (size_t)std::max<uint32_t>(n_prims, 1));
+    std::vector<double> h64(10 * (size_t)std::max<uint32_t>(n_prims, 1), 0.0);
+    for (size_t k = 0; k < bvh.prim_order.size(); k++) {
+      uint32_t id = bvh.prim_order[k];
+      const BdptPrim& p = prims[id];
+      const double* d = p.data;
+      for (int a = 0; a < 9; a++) h64[10 * k + a] = d[a];  // triangle p1 p2 p3 / sphere centre, radius
+      if (p.type == BDPT_PRIM_TRIANGLE) {
+        float v0[3], v1[3], v2[3];
+        for (int a = 0; a < 3; a++) { v0[a] = (float)d[a]; v1[a] = (float)d[3 + a]; v2[a] = (float)d[6 + a]; }
+        hp[3 * k + 0] = make_float4(v0[0], v0[1], v0[2], ibits((int)id));
+        hp[3 * k + 1] = make_float4(v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2], ibits(p.material));
+        hp[3 * k + 2] = make_float4(v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2], 0.f);
+        hs[3 * k + 0] = make_float4((float)d[9], (float)d[10], (float)d[11], 0.f);
+        hs[3 * k + 1] = make_float4((float)d[12], (float)d[13], (float)d[14], 0.f);
+        hs[3 * k + 2] = make_float4((float)d[15], (float)d[16], (float)d[17], 0.f);
+      } else {
+        float r = (float)d[3];
+        hp[3 * k + 0] = make_float4((float)d[0], (float)d[1], (float)d[2], ibits((int)id));
+        hp[3 * k + 1] = make_float4(r, (float)(d[3] * d[3]), 0.f, ibits(p.material | (int)0x80000000));
+        hp[3 * k + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        hs[3 * k + 0] = hs[3 * k + 1] = hs[3 * k + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    CK(ensure((void**)&ctx->d_nodes, &ctx->cap_scene[0], bvh.nodes.size() * sizeof(uint32_t)));
+    CK(ensure((void**)&ctx->d_prims, &ctx->cap_scene[1], hp.size() * sizeof(float4)));
+    CK(ensure((void**)&ctx->d_shading, &ctx->cap_scene[2], hs.size() * sizeof(float4)));
+    CK(ensure((void**)&ctx->d_prims64, &ctx->cap_scene[5], h64.size() * sizeof(double)));
+    CK(cudaMemcpyAsync(ctx->d_prims64, h64.data(), h64.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_prims, hp.data(), hp.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_shading, hs.data(), hs.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // the staging vectors go out of scope
+    ctx->d_prim_order = nullptr;
+    n_nodes = (uint32_t)(bvh.nodes.size() / 20); depth = bvh.max_depth;
+  }
   CK(cudaStreamSynchronize(ctx->stream));
+  // (historical name: the whole scene ingest — build, records, copies — since the build moved to the device)
+  ctx->ms_bvh_build = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 
   ctx->sc.nodes = ctx->d_nodes; ctx->sc.prims = ctx->d_prims; ctx->sc.shading = ctx->d_shading; ctx->sc.prims64 = ctx->d_prims64;
   ctx->sc.materials = ctx->d_mats; ctx->sc.lights = ctx->d_lights;
   ctx->sc.n_lights = (int)n_lights; ctx->sc.n_materials = (int)n_materials;
   ctx->sc.qbias_bits = 0x47000000u;
-  ctx->sc.n_nodes = (int)(bvh.nodes.size() / 20); ctx->sc.n_prims = (int)n_prims;
-  ctx->bvh_nodes = (uint32_t)(bvh.nodes.size() / 20); ctx->bvh_depth = bvh.max_depth;
+  ctx->sc.n_nodes = (int)n_nodes; ctx->sc.n_prims = (int)n_prims;
+  ctx->bvh_nodes = n_nodes; ctx->bvh_depth = depth;
   ctx->sched = ctx->sched_req >= 0 ? ctx->sched_req : (ctx->bvh_nodes > 8 ? 1 : 0);
   // what this scene promises the specialised kernels (common.cuh, BDPT_TRAIT_*)
   int traits = BDPT_TRAIT_TRIS | BDPT_TRAIT_LAMBERT;
@@ -687,7 +824,9 @@ int bdpt_host_build_bvh(const BdptPrim* prims, uint32_t n_prims, uint32_t* nodes
   std::vector<BuildPrim> bp;
   make_build_prims(prims, n_prims, &bp);
   Bvh8 bvh;
-  build_bvh8(bp, &bvh);
+  // BDPT_BVH_HOST_ALGO=ploc: the host restatement of the device build (bvh8.cpp, build_bvh8_ploc)
+  const char* algo = getenv("BDPT_BVH_HOST_ALGO");
+  if (algo && !strcmp(algo, "ploc")) build_bvh8_ploc(bp, &bvh); else build_bvh8(bp, &bvh);
   uint32_t nn = (uint32_t)(bvh.nodes.size() / 20);
   if (n_nodes) *n_nodes = nn;
   if (max_depth) *max_depth = bvh.max_depth;
@@ -696,6 +835,26 @@ int bdpt_host_build_bvh(const BdptPrim* prims, uint32_t n_prims, uint32_t* nodes
     memcpy(nodes_out, bvh.nodes.data(), bvh.nodes.size() * sizeof(uint32_t));
   }
   if (prim_order_out) memcpy(prim_order_out, bvh.prim_order.data(), bvh.prim_order.size() * sizeof(uint32_t));
+  return BDPT_OK;
+}
+
+int bdpt_device_bvh(BdptContext* ctx, uint32_t* nodes_out, uint32_t nodes_cap, uint32_t* n_nodes, uint32_t* prim_order_out,
+                    uint32_t* max_depth, uint32_t* rounds) {
+  int rc = check_ready(ctx, false);
+  if (rc) return rc;
+  CK(cudaSetDevice(ctx->device));
+  if (n_nodes) *n_nodes = ctx->bvh_nodes;
+  if (max_depth) *max_depth = ctx->bvh_depth;
+  if (rounds) *rounds = ctx->d_prim_order ? ctx->bvh_rounds : 0;
+  if (nodes_out) {
+    if (nodes_cap < ctx->bvh_nodes) return fail(ctx, BDPT_ERR_ARG, "nodes_cap too small");
+    CK(cudaMemcpyAsync(nodes_out, ctx->d_nodes, (size_t)ctx->bvh_nodes * 80, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (prim_order_out) {
+    if (!ctx->d_prim_order) return fail(ctx, BDPT_ERR_ARG, "the scene was built on the host (BDPT_BVH=host): use bdpt_host_build_bvh");
+    CK(cudaMemcpyAsync(prim_order_out, ctx->d_prim_order, (size_t)ctx->sc.n_prims * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
   return BDPT_OK;
 }
 

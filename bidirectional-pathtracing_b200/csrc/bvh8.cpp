@@ -2,6 +2,7 @@
 // quantisation.  Host code; see bvh8.h for the node layout and for how this relates to the
 // reference's BVHAccel (reference src/scene/bvh.cpp:51-129).
 #include "bvh8.h"
+#include "bvh_ploc.h"
 
 #include <algorithm>
 #include <cfloat>
@@ -208,7 +209,71 @@ struct Builder {
   }
 };
 
-inline uint32_t fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+// ---- tree views for bvh8_wide.h
+struct SahView {
+  const Builder& B;
+  void box(int n, float* lo, float* hi) const { for (int a = 0; a < 3; a++) { lo[a] = B.bn[n].box.lo[a]; hi[a] = B.bn[n].box.hi[a]; } }
+  int left(int n) const { return B.bn[n].left; }
+  int right(int n) const { return B.bn[n].right; }
+  int count(int n) const { return B.bn[n].count; }
+  void gather(int n, uint32_t* out) const { for (int i = 0; i < B.bn[n].count; i++) out[i] = B.idx[B.bn[n].first + i]; }
+};
+
+// Binary tree as flat arrays: what the device builder produces (bvh_gpu.cuh) and build_bvh8_ploc restates on the host.
+struct FlatView {
+  const float* lo4; const float* hi4;      // 4 floats per node
+  const int* l; const int* r; const int* cnt;
+  const uint32_t* leaf_prim;               // nodes [0, n_leaves) are the leaves: their primitive
+  void box(int n, float* lo, float* hi) const { for (int a = 0; a < 3; a++) { lo[a] = lo4[4 * (size_t)n + a]; hi[a] = hi4[4 * (size_t)n + a]; } }
+  int left(int n) const { return l[n]; }
+  int right(int n) const { return r[n]; }
+  int count(int n) const { return cnt[n]; }
+  void gather(int n, uint32_t* out) const {   // at most 3 primitives: a subtree of at most 5 nodes
+    int st[4], sp = 0, k = 0;
+    st[sp++] = n;
+    while (sp > 0) {
+      const int c = st[--sp];
+      if (l[c] < 0) out[k++] = leaf_prim[c];
+      else { st[sp++] = r[c]; st[sp++] = l[c]; }
+    }
+  }
+};
+
+// The collapse and the emission, for any tree view: SAH-optimal cut into 8-wide nodes bottom-up (`order`: parents
+// before children), then the wide nodes breadth first (children in slot order get consecutive node indices).
+template <class T>
+void emit_wide_tree(const T& view, int root, const std::vector<int>& order, int n_bin, const WideParams& P, Bvh8* out) {
+  std::vector<float> C((size_t)n_bin * 8, FLT_MAX);          // C[n*8 + i], i = 1..7
+  std::vector<uint8_t> split((size_t)n_bin * 9, 0);          // split[n*9 + j], j = 2..8
+  std::vector<uint8_t> is_leaf((size_t)n_bin, 0);            // the one-root form of n is a leaf child
+  for (size_t oi = order.size(); oi-- > 0;) wide_dp_node(view, order[oi], P, C.data(), split.data(), is_leaf.data());   // children before parents
+  struct Item { int wide; int bnode; uint32_t depth; };
+  std::deque<Item> queue;
+  out->nodes.assign(20, 0u);
+  out->prim_order.assign((size_t)view.count(root), 0u);
+  uint32_t n_prims_out = 0;
+  queue.push_back({0, root, 1});
+  while (!queue.empty()) {
+    Item it = queue.front(); queue.pop_front();
+    out->max_depth = std::max(out->max_depth, it.depth);
+    WidePlan plan;
+    wide_plan_node(view, split.data(), is_leaf.data(), it.bnode, &plan);
+    const uint32_t child_base = (uint32_t)(out->nodes.size() / 20);
+    const uint32_t prim_base = n_prims_out;
+    n_prims_out += (uint32_t)plan.n_leaf_prims;
+    out->nodes.resize(out->nodes.size() + 20 * (size_t)plan.n_internal, 0u);
+    int next_bn[8];
+    wide_write_node(view, is_leaf.data(), it.bnode, plan, child_base, prim_base, &out->nodes[(size_t)it.wide * 20], out->prim_order.data(), next_bn);
+    for (int k = 0; k < plan.n_internal; k++) queue.push_back({(int)child_base + k, next_bn[k], it.depth + 1});
+  }
+}
+
+WideParams wide_params_from_env() {
+  WideParams P; P.max_leaf = 3; P.prim_cost = 0.8f;   // 0.4 ... 1.0: within 1.5 % (measured on B200, round 1)
+  if (const char* e = getenv("BDPT_BVH_LEAF")) P.max_leaf = std::max(1, std::min(3, atoi(e)));   // tuning knobs
+  if (const char* e = getenv("BDPT_BVH_CP")) P.prim_cost = (float)atof(e);
+  return P;
+}
 
 }  // namespace
 
@@ -220,186 +285,85 @@ void build_bvh8(const std::vector<BuildPrim>& prims, Bvh8* out) {
   auto T1 = std::chrono::steady_clock::now();
   int root = B.build(0, (int)prims.size());
   auto T2 = std::chrono::steady_clock::now();
-
-  // ---- SAH-optimal collapse of the binary tree into 8-wide nodes (Ylitie, Karras, Laine 2017, section 3.2).
-  // C(n, i): cheapest way to represent the subtree of binary node n as at most i roots (i = 1..7).  One root is
-  // either a leaf child (<= kMaxLeaf primitives) or a wide node whose <= 8 children are the roots its two subtrees
-  // are distributed into:  C(n,1) = min(A_n P_n c_p,  A_n + min_k C(l,k) + C(r,8-k)),
-  // C(n,i) = min(C(n,i-1), min_k C(l,k) + C(r,i-k)).  The greedy "open the largest child" collapse this replaces
-  // left the average node half empty (4.1 of 8 slots on CBbunny, a quarter of the nodes with two children).
   const int nbn = B.next_node.load();
-  std::vector<float> C((size_t)nbn * 8, FLT_MAX);          // C[n*8 + i], i = 1..7
-  std::vector<uint8_t> split((size_t)nbn * 9, 0);          // split[n*9 + j], j = 2..8: roots given to the left subtree; 0 = "use j-1 roots"
-  std::vector<uint8_t> is_leaf((size_t)nbn, 0);            // the one-root form of n is a leaf child
+  std::vector<int> order; order.reserve(nbn);
   {
-    std::vector<int> order; order.reserve(nbn);
     std::vector<int> st; st.push_back(root);
     while (!st.empty()) { int n = st.back(); st.pop_back(); order.push_back(n); if (B.bn[n].left >= 0) { st.push_back(B.bn[n].left); st.push_back(B.bn[n].right); } }
-    for (size_t oi = order.size(); oi-- > 0;) {            // children before parents
-      const int n = order[oi];
-      const BNode& bnode = B.bn[n];
-      const float A = bnode.box.half_area();
-      float* c = &C[(size_t)n * 8];
-      if (bnode.left < 0) {                                // a single primitive
-        for (int i = 1; i <= 7; i++) c[i] = A * B.kPrimCost;
-        is_leaf[n] = 1;
-        continue;
-      }
-      const float* cl = &C[(size_t)bnode.left * 8];
-      const float* cr = &C[(size_t)bnode.right * 8];
-      uint8_t* sp = &split[(size_t)n * 9];
-      float dist[9];
-      for (int j = 2; j <= 8; j++) {
-        float best = FLT_MAX; int bk = 1;
-        for (int k = std::max(1, j - 7); k <= std::min(7, j - 1); k++) {
-          float v = cl[k] + cr[j - k];
-          if (v < best) { best = v; bk = k; }
-        }
-        dist[j] = best; sp[j] = (uint8_t)bk;
-      }
-      const float c_leaf = bnode.count <= B.kMaxLeaf ? A * (float)bnode.count * B.kPrimCost : FLT_MAX;
-      const float c_int = dist[8] + A;
-      if (c_leaf <= c_int) { c[1] = c_leaf; is_leaf[n] = 1; } else { c[1] = c_int; }
-      for (int i = 2; i <= 7; i++) {
-        if (dist[i] < c[i - 1]) c[i] = dist[i];
-        else { c[i] = c[i - 1]; sp[i] = 0; }
-      }
-    }
   }
-  // the roots that represent binary node n with a budget of i
-  struct Collect {
-    const Builder& B; const std::vector<uint8_t>& split;
-    void run(int n, int i, int* out, int& nout) const {
-      while (i > 1 && B.bn[n].left >= 0 && split[(size_t)n * 9 + i] == 0) i--;
-      if (i == 1 || B.bn[n].left < 0) { out[nout++] = n; return; }
-      const int k = split[(size_t)n * 9 + i];
-      run(B.bn[n].left, k, out, nout);
-      run(B.bn[n].right, i - k, out, nout);
-    }
-  } collect{B, split};
-
-  auto T2b = std::chrono::steady_clock::now();
-  struct Item { int wide; int bnode; uint32_t depth; };
-  std::deque<Item> queue;
-  out->nodes.assign(20, 0u);
-  queue.push_back({0, root, 1});
-  while (!queue.empty()) {
-    Item it = queue.front(); queue.pop_front();
-    out->max_depth = std::max(out->max_depth, it.depth);
-    const BNode& top = B.bn[it.bnode];
-    int ch[8]; int nch = 0;
-    if (top.left < 0) { ch[nch++] = it.bnode; }            // a one-primitive scene
-    else {
-      const int k = split[(size_t)it.bnode * 9 + 8];
-      collect.run(top.left, k, ch, nch);
-      collect.run(top.right, 8 - k, ch, nch);
-    }
-    // octant slot assignment (greedy maximum of centroid offset . slot direction)
-    float nc[3];
-    for (int a = 0; a < 3; a++) nc[a] = 0.5f * (top.box.lo[a] + top.box.hi[a]);
-    float cost[8][8];
-    for (int c = 0; c < nch; c++) {
-      const Box& b = B.bn[ch[c]].box;
-      float off[3];
-      for (int a = 0; a < 3; a++) off[a] = 0.5f * (b.lo[a] + b.hi[a]) - nc[a];
-      for (int s = 0; s < 8; s++)
-        cost[c][s] = ((s & 1) ? off[0] : -off[0]) + ((s & 2) ? off[1] : -off[1]) + ((s & 4) ? off[2] : -off[2]);
-    }
-    int slot_child[8]; for (int s = 0; s < 8; s++) slot_child[s] = -1;
-    {
-      // optimal assignment (maximum total of cost[child][slot]): Hungarian method on the 8 x 8 matrix, absent
-      // children padded with zero rows
-      const int N = 8;
-      double a[N + 1][N + 1];
-      for (int i = 1; i <= N; i++) for (int j = 1; j <= N; j++) a[i][j] = i <= nch ? -(double)cost[i - 1][j - 1] : 0.0;
-      double u[N + 1] = {0}, v[N + 1] = {0}; int pm[N + 1] = {0}, way[N + 1] = {0};
-      for (int i = 1; i <= N; i++) {
-        pm[0] = i; int j0 = 0; double minv[N + 1]; bool used[N + 1];
-        for (int j = 0; j <= N; j++) { minv[j] = 1e300; used[j] = false; }
-        do {
-          used[j0] = true; int i0 = pm[j0], j1 = 0; double delta = 1e300;
-          for (int j = 1; j <= N; j++) if (!used[j]) {
-            double cur = a[i0][j] - u[i0] - v[j];
-            if (cur < minv[j]) { minv[j] = cur; way[j] = j0; }
-            if (minv[j] < delta) { delta = minv[j]; j1 = j; }
-          }
-          for (int j = 0; j <= N; j++) if (used[j]) { u[pm[j]] += delta; v[j] -= delta; } else minv[j] -= delta;
-          j0 = j1;
-        } while (pm[j0] != 0);
-        do { int j1 = way[j0]; pm[j0] = pm[j1]; j0 = j1; } while (j0);
-      }
-      for (int j = 1; j <= N; j++) if (pm[j] >= 1 && pm[j] <= nch) slot_child[j - 1] = pm[j] - 1;
-    }
-    // quantisation grid.  Every decoded plane keeps at least 1/64 of a quantum of slack to the box it
-    // bounds (the grid origin sits 1/32 quantum below the node's min corner): the traversal decodes a
-    // plane as fma(2^15 + q, a, b - 2^15 a), whose rounding error is below 1/512 quantum (traverse.cuh).
-    float p[3]; uint32_t ebyte[3]; float scale[3], slack[3];
-    for (int a = 0; a < 3; a++) {
-      const float lo = top.box.lo[a], hi = top.box.hi[a];
-      float ext = hi - lo;
-      int e = -126;
-      if (ext > 0.f) {
-        e = (int)std::ceil(std::log2((double)ext / 254.9));
-        e = std::max(-126, std::min(126, e));
-      }
-      for (;; e++) {
-        scale[a] = std::ldexp(1.0f, e);
-        slack[a] = scale[a] * (1.0f / 64.0f);
-        p[a] = lo - 2.0f * slack[a];
-        if (e >= 126 || p[a] + 255.0f * scale[a] >= hi + slack[a]) break;
-      }
-      ebyte[a] = (uint32_t)(e + 127);
-    }
-    uint8_t meta[8] = {0}, q[6][8];
-    memset(q, 0, sizeof q);
-    uint32_t imask = 0;
-    uint32_t child_base = (uint32_t)(out->nodes.size() / 20);
-    uint32_t prim_base = (uint32_t)out->prim_order.size();
-    uint32_t prim_off = 0;
-    for (int s = 0; s < 8; s++) {
-      int c = slot_child[s];
-      if (c < 0) continue;
-      const BNode& cn = B.bn[ch[c]];
-      for (int a = 0; a < 3; a++) {
-        double lo = ((double)cn.box.lo[a] - (double)p[a]) / (double)scale[a];
-        double hi = ((double)cn.box.hi[a] - (double)p[a]) / (double)scale[a];
-        int qlo = (int)std::floor(lo), qhi = (int)std::ceil(hi);
-        qlo = std::max(0, std::min(255, qlo)); qhi = std::max(0, std::min(255, qhi));
-        // keep the decoded box conservative in fp32, with the slack the traversal's decode relies on
-        while (qlo > 0 && p[a] + (float)qlo * scale[a] > cn.box.lo[a] - slack[a]) qlo--;
-        while (qhi < 255 && p[a] + (float)qhi * scale[a] < cn.box.hi[a] + slack[a]) qhi++;
-        q[a][s] = (uint8_t)qlo; q[3 + a][s] = (uint8_t)qhi;
-      }
-      if (!is_leaf[ch[c]]) {
-        imask |= 1u << s;
-        meta[s] = (uint8_t)(0x20 | (24 + s));
-      } else {
-        uint32_t unary = cn.count == 1 ? 1u : cn.count == 2 ? 3u : 7u;
-        meta[s] = (uint8_t)((unary << 5) | prim_off);
-        for (int i = 0; i < cn.count; i++) out->prim_order.push_back(B.idx[cn.first + i]);
-        prim_off += (uint32_t)cn.count;
-      }
-    }
-    // children in slot order get consecutive node indices
-    for (int s = 0; s < 8; s++) {
-      if (!(imask & (1u << s))) continue;
-      int wide = (int)(out->nodes.size() / 20);
-      out->nodes.resize(out->nodes.size() + 20, 0u);
-      queue.push_back({wide, ch[slot_child[s]], it.depth + 1});
-    }
-    uint32_t* w = &out->nodes[(size_t)it.wide * 20];
-    w[0] = fbits(p[0]); w[1] = fbits(p[1]); w[2] = fbits(p[2]);
-    w[3] = ebyte[0] | (ebyte[1] << 8) | (ebyte[2] << 16) | (imask << 24);
-    w[4] = child_base; w[5] = prim_base;
-    auto pack4 = [](const uint8_t* b) { return (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24); };
-    w[6] = pack4(meta); w[7] = pack4(meta + 4);
-    for (int r = 0; r < 6; r++) { w[8 + 2 * r] = pack4(q[r]); w[9 + 2 * r] = pack4(q[r] + 4); }
-  }
+  WideParams P; P.max_leaf = B.kMaxLeaf; P.prim_cost = B.kPrimCost;
+  SahView view{B};
+  emit_wide_tree(view, root, order, nbn, P, out);
   if (getenv("BDPT_BVH_TIMING")) {
     auto T3 = std::chrono::steady_clock::now();
     auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-    fprintf(stderr, "bvh8: setup %.1f ms, sah %.1f ms, collapse dp %.1f ms, emit %.1f ms\n", ms(T0, T1), ms(T1, T2), ms(T2, T2b), ms(T2b, T3));
+    fprintf(stderr, "bvh8: setup %.1f ms, sah %.1f ms, collapse + emit %.1f ms\n", ms(T0, T1), ms(T1, T2), ms(T2, T3));
   }
+}
+
+// Host restatement of the DEVICE build (bvh_gpu.cuh): the same per-element steps (bvh_ploc.h, bvh8_wide.h) run as
+// plain loops.  It exists so that the CPU tests can check the algorithm's logic — tree soundness, quality against the
+// binned-SAH build — where there is no GPU; the product builds on the device.
+void build_bvh8_ploc(const std::vector<BuildPrim>& prims, Bvh8* out) {
+  out->nodes.clear(); out->prim_order.clear(); out->max_depth = 1;
+  const int N = (int)prims.size();
+  if (N == 0) { out->nodes.assign(20, 0u); return; }
+  // Morton order of the centroids
+  float clo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, chi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  std::vector<float> cent((size_t)N * 3);
+  for (int i = 0; i < N; i++)
+    for (int a = 0; a < 3; a++) {
+      const float c = 0.5f * (prims[i].lo[a] + prims[i].hi[a]);
+      cent[3 * (size_t)i + a] = c; clo[a] = std::min(clo[a], c); chi[a] = std::max(chi[a], c);
+    }
+  std::vector<std::pair<uint64_t, uint32_t>> keys(N);
+  for (int i = 0; i < N; i++) keys[i] = {ploc_morton(&cent[3 * (size_t)i], clo, chi), (uint32_t)i};
+  std::stable_sort(keys.begin(), keys.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+  const int n_bin = 2 * N - 1;
+  std::vector<float> lo4((size_t)n_bin * 4, 0.f), hi4((size_t)n_bin * 4, 0.f);
+  std::vector<int> l(n_bin, -1), r(n_bin, -1), cnt(n_bin, 1);
+  std::vector<uint32_t> leaf_prim(N);
+  for (int k = 0; k < N; k++) {
+    const BuildPrim& p = prims[keys[k].second];
+    leaf_prim[k] = keys[k].second;
+    for (int a = 0; a < 3; a++) { lo4[4 * (size_t)k + a] = p.lo[a]; hi4[4 * (size_t)k + a] = p.hi[a]; }
+  }
+  // PLOC rounds over the cluster array (cluster boxes kept in array order, as the device does)
+  std::vector<int> cluster(N), next_cluster(N), nn(N);
+  std::vector<float> clo4((size_t)N * 4), chi4((size_t)N * 4), nlo4((size_t)N * 4), nhi4((size_t)N * 4);
+  for (int k = 0; k < N; k++) { cluster[k] = k; for (int a = 0; a < 4; a++) { clo4[4 * (size_t)k + a] = lo4[4 * (size_t)k + a]; chi4[4 * (size_t)k + a] = hi4[4 * (size_t)k + a]; } }
+  int n = N, next_node = N;
+  while (n > 1) {
+    for (int i = 0; i < n; i++) nn[i] = ploc_nearest(i, n, clo4.data(), chi4.data());
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+      const int j = nn[i];
+      const bool mutual = nn[j] == i;
+      if (mutual && i > j) continue;       // merged into position j
+      int id = cluster[i];
+      float blo[4], bhi[4];
+      for (int a = 0; a < 4; a++) { blo[a] = clo4[4 * (size_t)i + a]; bhi[a] = chi4[4 * (size_t)i + a]; }
+      if (mutual) {
+        id = next_node++;
+        l[id] = cluster[i]; r[id] = cluster[j]; cnt[id] = cnt[cluster[i]] + cnt[cluster[j]];
+        for (int a = 0; a < 3; a++) { blo[a] = std::min(blo[a], clo4[4 * (size_t)j + a]); bhi[a] = std::max(bhi[a], chi4[4 * (size_t)j + a]); }
+        for (int a = 0; a < 4; a++) { lo4[4 * (size_t)id + a] = blo[a]; hi4[4 * (size_t)id + a] = bhi[a]; }
+      }
+      next_cluster[m] = id;
+      for (int a = 0; a < 4; a++) { nlo4[4 * (size_t)m + a] = blo[a]; nhi4[4 * (size_t)m + a] = bhi[a]; }
+      m++;
+    }
+    cluster.swap(next_cluster); clo4.swap(nlo4); chi4.swap(nhi4);
+    n = m;
+  }
+  const int root = cluster[0];
+  std::vector<int> order; order.reserve(n_bin);
+  {
+    std::vector<int> st; st.push_back(root);
+    while (!st.empty()) { int c = st.back(); st.pop_back(); order.push_back(c); if (l[c] >= 0) { st.push_back(l[c]); st.push_back(r[c]); } }
+  }
+  FlatView view{lo4.data(), hi4.data(), l.data(), r.data(), cnt.data(), leaf_prim.data()};
+  emit_wide_tree(view, root, order, n_bin, wide_params_from_env(), out);
 }
 
 }  // namespace bdpt

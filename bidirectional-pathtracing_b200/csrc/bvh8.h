@@ -36,7 +36,10 @@ struct Bvh8 {
   uint32_t max_depth = 0;
 };
 
-// Builds the tree. Never fails for n >= 1; n == 0 yields a single empty node.
+// Host build (binned SAH, top down).  Never fails for n >= 1; n == 0 yields a single empty node.  Since round 2 the
+// product builds on the device (bvh_gpu.cuh); this one is the checker and the BDPT_BVH=host path.
 void build_bvh8(const std::vector<BuildPrim>& prims, Bvh8* out);
+// Host restatement of the device build (PLOC over Morton order + the same collapse): for the CPU tests.
+void build_bvh8_ploc(const std::vector<BuildPrim>& prims, Bvh8* out);
 
 }  // namespace bdpt

@@ -37,6 +37,28 @@ BDPT_HD inline float wide_half_area(const float* lo, const float* hi) {
 // distributed into:  C(n,1) = min(A_n P_n c_p,  A_n + min_k C(l,k) + C(r,8-k)),
 // C(n,i) = min(C(n,i-1), min_k C(l,k) + C(r,i-k)).
 // c = C + 8 n (entries 1..7), sp = split + 9 n (entries 2..8: roots given to the left subtree; 0 = "use one root fewer").
+// cl / cr: the children's rows (entries 1..7); c / sp / leaf: this node's outputs
+BDPT_HD inline void wide_dp_combine(float A, int cnt, const float* cl, const float* cr, const WideParams& P, float* c, uint8_t* sp,
+                                    uint8_t* leaf) {
+  float dist[9];
+  for (int j = 2; j <= 8; j++) {
+    float best = FLT_MAX; int bk = 1;
+    const int k0 = j - 7 > 1 ? j - 7 : 1, k1 = j - 1 < 7 ? j - 1 : 7;
+    for (int k = k0; k <= k1; k++) {
+      float v = cl[k] + cr[j - k];
+      if (v < best) { best = v; bk = k; }
+    }
+    dist[j] = best; sp[j] = (uint8_t)bk;
+  }
+  const float c_leaf = cnt <= P.max_leaf ? A * (float)cnt * P.prim_cost : FLT_MAX;
+  const float c_int = dist[8] + A;
+  if (c_leaf <= c_int) { c[1] = c_leaf; *leaf = 1; } else { c[1] = c_int; *leaf = 0; }
+  for (int i = 2; i <= 7; i++) {
+    if (dist[i] < c[i - 1]) c[i] = dist[i];
+    else { c[i] = c[i - 1]; sp[i] = 0; }
+  }
+}
+
 template <class T>
 BDPT_HD inline void wide_dp_node(const T& t, int n, const WideParams& P, float* C, uint8_t* split, uint8_t* is_leaf) {
   float lo[3], hi[3];
@@ -49,27 +71,7 @@ BDPT_HD inline void wide_dp_node(const T& t, int n, const WideParams& P, float* 
     is_leaf[n] = 1;
     return;
   }
-  const float* cl = C + (size_t)l * 8;
-  const float* cr = C + (size_t)t.right(n) * 8;
-  uint8_t* sp = split + (size_t)n * 9;
-  float dist[9];
-  for (int j = 2; j <= 8; j++) {
-    float best = FLT_MAX; int bk = 1;
-    const int k0 = j - 7 > 1 ? j - 7 : 1, k1 = j - 1 < 7 ? j - 1 : 7;
-    for (int k = k0; k <= k1; k++) {
-      float v = cl[k] + cr[j - k];
-      if (v < best) { best = v; bk = k; }
-    }
-    dist[j] = best; sp[j] = (uint8_t)bk;
-  }
-  const int cnt = t.count(n);
-  const float c_leaf = cnt <= P.max_leaf ? A * (float)cnt * P.prim_cost : FLT_MAX;
-  const float c_int = dist[8] + A;
-  if (c_leaf <= c_int) { c[1] = c_leaf; is_leaf[n] = 1; } else { c[1] = c_int; is_leaf[n] = 0; }
-  for (int i = 2; i <= 7; i++) {
-    if (dist[i] < c[i - 1]) c[i] = dist[i];
-    else { c[i] = c[i - 1]; sp[i] = 0; }
-  }
+  wide_dp_combine(A, t.count(n), C + (size_t)l * 8, C + (size_t)t.right(n) * 8, P, c, split + (size_t)n * 9, is_leaf + n);
 }
 
 // the roots that represent binary node n with a budget of i (iterative form of the recursion over `split`)

@@ -127,12 +127,18 @@ int bdpt_reduce_all(BdptContext** ctxs, int n, int root);
 int bdpt_comm_destroy(BdptContext* ctx);
 
 /* --- test hooks (parity against the oracle) ------------------------------------------------ */
-/* Host-only (needs no GPU): builds the 8-wide BVH exactly as bdpt_upload_scene does and returns it for
+/* Host-only (needs no GPU): builds the 8-wide BVH on the host — the binned-SAH build that BDPT_BVH=host uploads,
+ * or, with BDPT_BVH_HOST_ALGO=ploc, the host restatement of the device build's algorithm — and returns it for
  * inspection — 20 words per node (layout: bidirectional-pathtracing_b200/csrc/bvh8.h), the leaf order
  * (prim_order_out[k] = primitive index of leaf slot k, n_prims entries) and the tree depth.  Pass
  * nodes_out = NULL to query n_nodes first.  Stands where BVHAccel::construct_bvh does (bvh.cpp:51-129). */
 int bdpt_host_build_bvh(const BdptPrim* prims, uint32_t n_prims, uint32_t* nodes_out, uint32_t nodes_cap,
                         uint32_t* n_nodes, uint32_t* prim_order_out, uint32_t* max_depth);
+/* The tree bdpt_upload_scene built ON THE DEVICE for the current scene (Morton order + PLOC + the same 8-wide collapse,
+ * bidirectional-pathtracing_b200/csrc/bvh_gpu.cuh), copied back for inspection: same layout as above; *rounds = PLOC
+ * rounds it took.  Pass nodes_out = NULL to query n_nodes first. */
+int bdpt_device_bvh(BdptContext* ctx, uint32_t* nodes_out, uint32_t nodes_cap, uint32_t* n_nodes, uint32_t* prim_order_out,
+                    uint32_t* max_depth, uint32_t* rounds);
 /* rays: n x {o[3], d[3], tmin, tmax} fp64 -> hits: n x {prim id (-1 miss), t, n[3], material} fp64.
  * Mirrors BVHAccel::intersect (bvh.h:104-107). */
 int bdpt_intersect_batch(BdptContext* ctx, const double* rays, size_t n, double* hits);

