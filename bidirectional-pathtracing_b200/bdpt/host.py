@@ -18,6 +18,8 @@ def load_library():
         L = C.CDLL(LIB_PATH)
         L.bdpt_host_load_dae.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.POINTER(C.c_ubyte)), C.POINTER(C.c_size_t)]
         L.bdpt_host_load_dae.restype = C.c_int
+        L.bdpt_host_apply_camera_settings.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
+        L.bdpt_host_apply_camera_settings.restype = C.c_int
         L.bdpt_host_free.argtypes = [C.c_void_p]
         L.bdpt_host_free.restype = None
         L.bdpt_host_last_error.restype = C.c_char_p
@@ -36,3 +38,14 @@ def load_dae(path: str, width: int = 0, height: int = 0) -> fs.FlatScene:
         return fs.frombytes(C.string_at(blob, size.value))
     finally:
         L.bdpt_host_free(blob)
+
+
+def apply_camera_settings(scene: fs.FlatScene, path: str, width: int, height: int) -> fs.FlatScene:
+    """The reference's `-c <file>` (Camera::load_settings) on a copy of the scene's camera."""
+    import numpy as np
+    L = load_library()
+    cam = np.ascontiguousarray(scene.camera.copy())
+    rc = L.bdpt_host_apply_camera_settings(cam.ctypes.data, os.fsencode(path), width, height)
+    if rc != 0:
+        raise RuntimeError(f"bdpt_host_apply_camera_settings({path}) failed ({rc}): {L.bdpt_host_last_error().decode()}")
+    return fs.FlatScene(cam, scene.materials, scene.lights, scene.prims)

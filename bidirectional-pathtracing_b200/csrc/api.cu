@@ -55,6 +55,7 @@ struct BdptContext {
   float* resolve_tmp = nullptr;
   uint8_t* rgba_tmp = nullptr;
   int ns_last = 1;
+  int cell[4] = {0, 0, 0, 0};   // x, y, dx, dy of a cell render (bdpt_set_cell); dx = 0: the whole frame
 
   // batch storage
   size_t cap_B = 0; int cap_m = -1; size_t cap_q = 0;
@@ -233,8 +234,11 @@ void fill_job(BdptContext* ctx, const BdptRenderParams* p, Job* J) {
   J->acc_eye = ctx->acc_eye; J->acc_light = ctx->acc_light; J->stats = ctx->d_stats; J->dbg = nullptr;
   // the walk stores a vertex before it tests the depth (bidirection.cpp:82-86): m = 0 behaves as m = 1
   J->seed = p->seed; J->m = std::max(1, p->max_ray_depth); J->first_sample = p->first_sample;
-  J->tiles_x = (ctx->W + 7) / 8;
-  J->npix_pad = J->tiles_x * ((ctx->H + 3) / 4) * 32;
+  const bool cell = ctx->cell[2] > 0;
+  J->cx0 = cell ? ctx->cell[0] : 0; J->cy0 = cell ? ctx->cell[1] : 0;
+  J->cx1 = cell ? ctx->cell[0] + ctx->cell[2] : ctx->W; J->cy1 = cell ? ctx->cell[1] + ctx->cell[3] : ctx->H;
+  J->tiles_x = (J->cx1 - J->cx0 + 7) / 8;
+  J->npix_pad = J->tiles_x * ((J->cy1 - J->cy0 + 3) / 4) * 32;
   J->div_tiles_x = make_fastdiv((uint32_t)J->tiles_x); J->div_npix_pad = make_fastdiv((uint32_t)J->npix_pad);
   J->roulette = (p->flags & BDPT_FLAG_ROULETTE) ? 1 : 0;
   J->no_mis = (p->flags & BDPT_FLAG_NO_MIS) ? 1 : 0;
@@ -412,10 +416,12 @@ int build_scene_on_device(BdptContext* ctx, const BdptPrim* prims, uint32_t n_pr
   CK(cudaMemcpyAsync(ctr, ctx->h_bvh, 4 * sizeof(unsigned), cudaMemcpyHostToDevice, st));
   // PLOC rounds; the cluster count comes back every few rounds (the kernels of a finished build are no-ops)
   int n_upper = N; uint32_t rounds = 0;
+  int radius = BDPT_PLOC_RADIUS;
+  if (const char* e = getenv("BDPT_PLOC_RADIUS")) radius = std::max(1, std::min(256, atoi(e)));   // tuning only
   while (n_upper > 1) {
     for (int r = 0; r < 4; r++) {
       const int g = (n_upper + BDPT_PLOC_BLOCK - 1) / BDPT_PLOC_BLOCK;
-      k_ploc_nearest<<<g, BDPT_PLOC_BLOCK, 0, st>>>(ctr, clo, chi, nn);
+      k_ploc_nearest<<<g, BDPT_PLOC_BLOCK, 0, st>>>(ctr, clo, chi, nn, radius);
       k_ploc_merge<<<g, BDPT_PLOC_BLOCK, 0, st>>>(ctr, nn, cluster, clo, chi, T, out_id, olo, ohi, keep, bcount);
       k_ploc_scan<<<1, 1024, 0, st>>>(ctr, bcount, boff);
       k_ploc_scatter<<<g, BDPT_PLOC_BLOCK, 0, st>>>(ctr, keep, boff, out_id, olo, ohi, cluster, clo, chi);
@@ -687,9 +693,19 @@ int bdpt_set_frame(BdptContext* ctx, int width, int height) {
     }
     ctx->acc_eye = ctx->acc; ctx->acc_light = ctx->acc + npix;
     ctx->W = width; ctx->H = height;
+    ctx->cell[0] = ctx->cell[1] = ctx->cell[2] = ctx->cell[3] = 0;
   }
   make_dcamera(ctx->cam_base, ctx->W, ctx->H, &ctx->cam);
   return bdpt_clear(ctx);
+}
+
+int bdpt_set_cell(BdptContext* ctx, int x, int y, int dx, int dy) {
+  if (!ctx) return BDPT_ERR_ARG;
+  if (dx == 0 && dy == 0) { ctx->cell[0] = ctx->cell[1] = ctx->cell[2] = ctx->cell[3] = 0; return BDPT_OK; }
+  if (ctx->W <= 0) return fail(ctx, BDPT_ERR_ARG, "no frame size set (bdpt_set_frame)");
+  if (x < 0 || y < 0 || dx <= 0 || dy <= 0 || x + dx > ctx->W || y + dy > ctx->H) return fail(ctx, BDPT_ERR_ARG, "cell outside the frame");
+  ctx->cell[0] = x; ctx->cell[1] = y; ctx->cell[2] = dx; ctx->cell[3] = dy;
+  return BDPT_OK;
 }
 
 int bdpt_clear(BdptContext* ctx) {
@@ -720,7 +736,8 @@ int bdpt_render(BdptContext* ctx, const BdptRenderParams* p) {
   size_t B = (size_t)((size_t)ctx->batch_gib << 30) / per_sample;
   B = std::min<size_t>(B, (size_t)1 << ctx->batch_log2);
   B = std::max<size_t>(B & ~(size_t)1023, 1024);
-  const int tiles_x = (ctx->W + 7) / 8, npix_pad = tiles_x * ((ctx->H + 3) / 4) * 32;
+  const int cw = ctx->cell[2] > 0 ? ctx->cell[2] : ctx->W, ch = ctx->cell[2] > 0 ? ctx->cell[3] : ctx->H;
+  const int tiles_x = (cw + 7) / 8, npix_pad = tiles_x * ((ch + 3) / 4) * 32;
   const unsigned long long total = (unsigned long long)npix_pad * (unsigned long long)p->n_samples;
   if (total < B) B = (size_t)((total + 1023) & ~1023ull);
   // If the device cannot give the slab (another context holds the memory), halve the batch until it can: the image
@@ -764,7 +781,7 @@ int bdpt_render(BdptContext* ctx, const BdptRenderParams* p) {
   ctx->stats.ms_walk = w; ctx->stats.ms_connect = c; ctx->stats.ms_shadow = s;
   ctx->stats.timed_batches = (uint32_t)timed; ctx->stats.n_batches = (uint32_t)n_batches;
   ctx->stats.batch_samples = (uint32_t)B;
-  ctx->stats.samples += (unsigned long long)ctx->W * ctx->H * (unsigned long long)p->n_samples;
+  ctx->stats.samples += (unsigned long long)cw * ch * (unsigned long long)p->n_samples;
   if (ctx->h_qctr[4]) return fail(ctx, BDPT_ERR_OVERFLOW, "shadow queue overflow");
   return BDPT_OK;
 }

@@ -95,11 +95,11 @@ __global__ void k_bvh_leaves(const float4* blo, const float4* bhi, const uint32_
 }
 
 // ---- one PLOC round.  ctr: [0] clusters now  [1] clusters after this round  [2] next free node id
-__global__ void k_ploc_nearest(const unsigned* ctr, const float4* clo, const float4* chi, int* nn) {
+__global__ void k_ploc_nearest(const unsigned* ctr, const float4* clo, const float4* chi, int* nn, int radius) {
   const int n = (int)ctr[0];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || n < 2) return;
-  nn[i] = ploc_nearest(i, n, (const float*)clo, (const float*)chi);
+  nn[i] = ploc_nearest(i, n, (const float*)clo, (const float*)chi, radius);
 }
 
 #define BDPT_PLOC_BLOCK 256

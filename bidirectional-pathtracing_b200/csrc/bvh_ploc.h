@@ -42,11 +42,11 @@ BDPT_HD inline uint64_t ploc_morton(const float* c, const float* clo, const floa
 // Nearest neighbour of cluster position i among positions [i - R, i + R]: the one minimising the half area of the
 // union box; ties by the pair's (lower, higher) position, so that the globally best pair always picks each other and
 // every round merges at least one pair.  lo / hi: boxes of the clusters in ARRAY order, 4 floats apiece.
-BDPT_HD inline int ploc_nearest(int i, int n, const float* lo4, const float* hi4) {
+BDPT_HD inline int ploc_nearest(int i, int n, const float* lo4, const float* hi4, int radius = BDPT_PLOC_RADIUS) {
   const float* li = lo4 + 4 * (size_t)i; const float* hi_ = hi4 + 4 * (size_t)i;
   int best = -1; float best_a = FLT_MAX; int best_lo = 0, best_hi = 0;
-  const int j0 = i - BDPT_PLOC_RADIUS > 0 ? i - BDPT_PLOC_RADIUS : 0;
-  const int j1 = i + BDPT_PLOC_RADIUS < n - 1 ? i + BDPT_PLOC_RADIUS : n - 1;
+  const int j0 = i - radius > 0 ? i - radius : 0;
+  const int j1 = i + radius < n - 1 ? i + radius : n - 1;
   for (int j = j0; j <= j1; j++) {
     if (j == i) continue;
     const float* lj = lo4 + 4 * (size_t)j; const float* hj = hi4 + 4 * (size_t)j;

@@ -58,7 +58,8 @@ struct Job {
   int B;                      // samples in this batch
   int m;                      // max_ray_depth
   int first_sample;           // sample index of job-sample 0
-  int tiles_x, npix_pad;      // 8x4 pixel tiles per row; padded pixel count
+  int tiles_x, npix_pad;      // 8x4 pixel tiles per row; padded pixel count (of the cell)
+  int cx0, cy0, cx1, cy1;     // the pixels that are sampled: the frame, or the cell of a cell render
   FastDiv div_tiles_x, div_npix_pad;
   int roulette;
   int ntop;                   // BVH nodes staged in shared memory by the persistent kernels
@@ -80,10 +81,10 @@ __device__ inline bool decode_sample(const Job& J, unsigned long long g, int* x,
   int p = (int)(q - qd * (unsigned int)J.npix_pad);
   int tile = p >> 5, w = p & 31;
   const int ty = (int)fast_div((unsigned int)tile, J.div_tiles_x), tx = tile - ty * J.tiles_x;
-  *x = tx * 8 + (w & 7);
-  *y = ty * 4 + (w >> 3);
+  *x = J.cx0 + tx * 8 + (w & 7);
+  *y = J.cy0 + ty * 4 + (w >> 3);
   *sample = J.first_sample + (int)k;
-  return *x < J.cam.W && *y < J.cam.H;
+  return *x < J.cx1 && *y < J.cy1;
 }
 
 // float4 index of the first quarter of the 64-byte record of vertex j of subpath (kind, i)

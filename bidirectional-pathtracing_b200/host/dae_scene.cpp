@@ -676,6 +676,25 @@ void apply_screen_size(BdptCamera* cam, int w, int h) {  // Camera::set_screen_s
   cam->vfov_deg = 2 * (std::atan(((double)h) / (2 * cam->screen_dist)) * (180 / PI));
 }
 
+bool apply_camera_settings(BdptCamera* cam, const std::string& path, int w, int h, std::string* err) {
+  FILE* f = fopen(path.c_str(), "r");
+  if (!f) { if (err) *err = "cannot open camera settings file " + path; return false; }
+  double v[30];
+  int n = 0;
+  while (n < 30 && fscanf(f, "%lf", &v[n]) == 1) n++;
+  fclose(f);
+  if (n < 28) { if (err) *err = "camera settings file " + path + " is too short"; return false; }
+  // hFov vFov ar nClip fClip | pos[3] target[3] | phi theta r minR maxR | c2w(row, col) x 9 | screenW screenH screenDist | focalDistance lensRadius
+  cam->hfov_deg = v[0]; cam->vfov_deg = v[1]; cam->nclip = v[3]; cam->fclip = v[4];
+  for (int i = 0; i < 3; i++) { cam->pos[i] = v[5 + i]; cam->target[i] = v[8 + i]; }
+  for (int i = 0; i < 9; i++) cam->c2w[3 * (i % 3) + i / 3] = v[16 + i];   // file: row-major; BdptCamera: three column vectors
+  cam->screen_dist = v[27];
+  // the frame keeps its size; with screen_w/h equal to it the library does not re-derive the fovs (camera.cpp:83-89)
+  cam->screen_w = w > 0 ? w : v[25];
+  cam->screen_h = h > 0 ? h : v[26];
+  return true;
+}
+
 std::vector<unsigned char> serialize(const FlatSceneData& s) {
   BdptSceneHeader h; memset(&h, 0, sizeof h);
   h.magic = BDPT_FSCENE_MAGIC; h.n_prims = (uint32_t)s.prims.size(); h.n_materials = (uint32_t)s.materials.size(); h.n_lights = (uint32_t)s.lights.size();

@@ -25,6 +25,11 @@ int bdpt_host_load_dae(const char* path, int width, int height, unsigned char** 
   return 0;
 }
 
+int bdpt_host_apply_camera_settings(void* camera, const char* path, int width, int height) {
+  if (!camera || !path) return -2;
+  return bdpt_host::apply_camera_settings((BdptCamera*)camera, path, width, height, &g_err) ? 0 : -3;
+}
+
 void bdpt_host_free(void* p) { free(p); }
 const char* bdpt_host_last_error(void) { return g_err.c_str(); }
 

@@ -3,9 +3,11 @@
 // Keeps the reference's windowless surface (reference src/application/main.cpp:79-182):
 //     pathtracer [-s spp] [-m max_ray_depth] [-t threads] [-r W H] -f out.png scene.dae
 // -s / -m / -r / -f mean what they mean there; -t is accepted and ignored (the GPU path has no host
-// worker threads); -l -a -b -d -H -c are accepted and ignored exactly as the reference's BDPT ignores
-// them; -e (environment map) and -p (cell render) are rejected: the reference's BDPT aborts on
-// environment lights (environment_light.cpp:182-208) and the cell path belongs to the GUI.
+// worker threads); -l -a -b -d -H are accepted and ignored exactly as the reference's BDPT ignores them;
+// -c <file> loads a camera settings file (Camera::load_settings, camera.cpp:169-186; applied after -r like
+// main.cpp:174-178); -p x y dx dy renders a cell and writes a dx x dy image (render_to_file's cell path,
+// raytraced_renderer.cpp:338-346); -e (environment map) is rejected: the reference's BDPT aborts on environment
+// lights (environment_light.cpp:182-208).
 // Extra options of this build: -g N (use N GPUs of this box: samples sharded, scene ingested per GPU in parallel
 // host threads, ONE ncclReduce of the accumulators to GPU 0), -S seed, -R (enable the roulette rule the reference ships
 // commented out), -B (balance heuristic), -o scene.fscene (dump the flat scene and exit).
@@ -34,6 +36,8 @@ static void usage(const char* bin) {
   printf("  -m  <INT>        Maximum ray depth\n");
   printf("  -f  <FILENAME>   Image (.png) file to save output to\n");
   printf("  -r  <INT> <INT>  Width and height of output image\n");
+  printf("  -p  <x> <y> <dx> <dy>  Used with -f and -r to render a cell\n");
+  printf("  -c  <FILENAME>   Load camera settings file (mainly to set camera position when windowless)\n");
   printf("  -g  <INT>        Number of GPUs to shard the samples over (default 1)\n");
   printf("  -S  <INT>        Random seed (default 0)\n");
   printf("  -R               Russian roulette (off in the reference)\n");
@@ -47,7 +51,8 @@ static void usage(const char* bin) {
 int main(int argc, char** argv) {
   int ns = 1, m = 1, threads = 1, W = 0, H = 0, gpus = 1, roulette = 0, balance = 0;
   unsigned long long seed = 0;
-  std::string out_png, out_fscene;
+  std::string out_png, out_fscene, cam_settings;
+  int cell_x = -1, cell_y = 0, cell_dx = 0, cell_dy = 0;
   int opt;
   while ((opt = getopt(argc, argv, "s:l:t:m:e:hH:f:r:c:b:d:a:p:g:S:RBo:")) != -1) {
     switch (opt) {
@@ -61,11 +66,16 @@ int main(int argc, char** argv) {
       case 'R': roulette = 1; break;
       case 'B': balance = 1; break;
       case 'o': out_fscene = optarg; break;
-      case 'l': case 'c': case 'b': case 'd': break;        // no effect on the BDPT image
+      case 'c': cam_settings = optarg; break;
+      case 'p':   // four arguments, parsed like main.cpp:97-103
+        if (optind + 2 >= argc) { usage(argv[0]); return 1; }
+        cell_x = atoi(argv[optind - 1]); cell_y = atoi(argv[optind]); cell_dx = atoi(argv[optind + 1]); cell_dy = atoi(argv[optind + 2]);
+        optind += 3;
+        break;
+      case 'l': case 'b': case 'd': break;                  // no effect on the BDPT image
       case 'a': optind++; break;                              // two arguments, ignored
       case 'H': optind--; break;                              // flag in the reference (main.cpp:131-134)
       case 'e': MSG("environment maps are not supported by the BDPT integrator (the reference aborts on them)"); return 1;
-      case 'p': MSG("cell rendering (-p) is a GUI feature and is not supported"); return 1;
       default: usage(argv[0]); return 1;
     }
   }
@@ -78,6 +88,13 @@ int main(int argc, char** argv) {
   std::string err;
   if (!bdpt_host::load_dae(scene_path, &scene, &err)) { MSG("Error: %s", err.c_str()); return 1; }
   if (W <= 0 || H <= 0) { W = 800; H = 600; }
+  if (!cam_settings.empty()) {
+    bdpt_host::apply_screen_size(&scene.camera, W, H);    // -r first, then the file (main.cpp:174-178)
+    if (!bdpt_host::apply_camera_settings(&scene.camera, cam_settings, W, H, &err)) { MSG("Error: %s", err.c_str()); return 1; }
+    printf("[Camera] Loaded settings from %s\n", cam_settings.c_str());
+  }
+  const bool cell = cell_x >= 0;
+  if (cell && (cell_dx <= 0 || cell_dy <= 0 || cell_y < 0 || cell_x + cell_dx > W || cell_y + cell_dy > H)) { MSG("Error: cell outside the frame"); return 1; }
   if (!out_fscene.empty()) {
     bdpt_host::apply_screen_size(&scene.camera, W, H);
     std::vector<unsigned char> b = bdpt_host::serialize(scene);
@@ -104,6 +121,7 @@ int main(int argc, char** argv) {
         int rc = bdpt_upload_scene(ctx[g], &scene.camera, scene.materials.data(), (uint32_t)scene.materials.size(), scene.lights.data(),
                                    (uint32_t)scene.lights.size(), scene.prims.data(), (uint32_t)scene.prims.size());
         if (rc == BDPT_OK) rc = bdpt_set_frame(ctx[g], W, H);
+        if (rc == BDPT_OK && cell) rc = bdpt_set_cell(ctx[g], cell_x, cell_y, cell_dx, cell_dy);
         rcs[g] = rc;
       });
     for (auto& t : th) t.join();
@@ -139,17 +157,33 @@ int main(int argc, char** argv) {
   fprintf(stdout, "\r[PathTracer] Rendering... 100%%! (%.4fs)\n", secs);
   fprintf(stdout, "[PathTracer] BVH traced %llu rays.\n", rays);
   fprintf(stdout, "[PathTracer] Average speed %.4f million rays per second.\n", (double)rays / secs * 1e-6);
-  fprintf(stdout, "[PathTracer] %.4f million BDPT samples per second.\n", (double)W * H * ns / secs * 1e-6);
+  fprintf(stdout, "[PathTracer] %.4f million BDPT samples per second.\n", (double)(cell ? cell_dx * cell_dy : W * H) * ns / secs * 1e-6);
+  int out_w = W, out_h = H;
+  if (cell) {
+    // raytrace_cell copies the cell out of the frame (raytraced_renderer.cpp:643-647) and save_image flips it: rows
+    // [H - y - dy, H - y) of the top-down image, columns [x, x + dx)
+    std::vector<uint8_t> crop((size_t)cell_dx * cell_dy * 4);
+    for (int r = 0; r < cell_dy; r++)
+      memcpy(&crop[(size_t)r * cell_dx * 4], &rgba[((size_t)(H - cell_y - cell_dy + r) * W + cell_x) * 4], (size_t)cell_dx * 4);
+    rgba.swap(crop); out_w = cell_dx; out_h = cell_dy;
+  }
   fprintf(stderr, "[PathTracer] Saving to file: %s... ", out_png.c_str());
-  if (!bdpt_host::write_png_rgba8(out_png, rgba.data(), W, H)) { fprintf(stderr, "failed\n"); return 1; }
+  if (!bdpt_host::write_png_rgba8(out_png, rgba.data(), out_w, out_h)) { fprintf(stderr, "failed\n"); return 1; }
   fprintf(stderr, "Done!\n");
   // save_sampling_rate_image (raytraced_renderer.cpp:730-761): every pixel received ns_aa samples -> rate 1 -> red
   if (out_png.size() > 4) {
     std::vector<uint8_t> rate((size_t)W * H * 4);
     for (size_t i = 0; i < (size_t)W * H; i++) { rate[4 * i] = 255; rate[4 * i + 1] = 0; rate[4 * i + 2] = 0; rate[4 * i + 3] = 255; }
-    bdpt_host::write_png_rgba8(out_png.substr(0, out_png.size() - 4) + "_rate.png", rate.data(), W, H);
+    if (cell)   // pixels outside the cell were not sampled: rate 0 -> blue
+      for (int yy = 0; yy < H; yy++)
+        for (int xx = 0; xx < W; xx++) {
+          const int fy = H - 1 - yy;   // frame row (0 = bottom) of image row yy
+          if (xx >= cell_x && xx < cell_x + cell_dx && fy >= cell_y && fy < cell_y + cell_dy) continue;
+          uint8_t* o = &rate[4 * ((size_t)yy * W + xx)]; o[0] = 0; o[1] = 0; o[2] = 255;
+        }
+    bdpt_host::write_png_rgba8(out_png.substr(0, out_png.size() - 4) + "_rate.png", rate.data(), W, H);   // always frame-sized (:737-760)
   }
   for (BdptContext* c : ctx) bdpt_destroy(c);
-  fprintf(stdout, "[PathTracer] Job completed.\n");
+  fprintf(stdout, cell ? "[PathTracer] Cell job completed.\n" : "[PathTracer] Job completed.\n");
   return 0;
 }

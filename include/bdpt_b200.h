@@ -98,6 +98,11 @@ int bdpt_set_frame(BdptContext* ctx, int width, int height);
 
 /* --- render : replaces start_raytracing + the worker threads' raytrace_pixel loop
  *     (raytraced_renderer.cpp:267-328,595-620; bidirection.cpp:503-542) -------------------- */
+/* Cell render, the reference's `-p x y dx dy` (RaytracedRenderer::render_to_file with a cell, raytraced_renderer.cpp:
+ * 330-347, tile queue over the cell :301-319): later bdpt_render calls sample only the pixels of [x, x+dx) x [y, y+dy)
+ * (row 0 = bottom); their light subpaths still splat anywhere in the frame.  dx = dy = 0 restores the whole frame, and so
+ * does bdpt_set_frame with a new size. */
+int bdpt_set_cell(BdptContext* ctx, int x, int y, int dx, int dy);
 int bdpt_clear(BdptContext* ctx);                               /* BidirectionalPathTracer::clear          */
 int bdpt_render(BdptContext* ctx, const BdptRenderParams* p);   /* accumulates; returns when the GPU is done */
 int bdpt_read_framebuffer(BdptContext* ctx, int which, float* rgb_out); /* D2H, already divided by ns_total  */

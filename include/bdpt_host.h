@@ -15,6 +15,10 @@ extern "C" {
 #endif
 /* 0 = ok; the blob is malloc'ed and must be released with bdpt_host_free. <0 = error (bdpt_host_last_error). */
 int bdpt_host_load_dae(const char* path, int width, int height, unsigned char** blob, size_t* size);
+/* Camera::load_settings (reference src/pathtracer/camera.cpp:169-186), the `-c <file>` option, applied to a BdptCamera
+ * (bdpt_flatscene.h) in place.  The reference loads the file AFTER `-r` (src/application/main.cpp:174-178): the file's
+ * fovs replace the ones Camera::set_screen_size derived; width / height are the frame the camera will render. */
+int bdpt_host_apply_camera_settings(void* camera, const char* path, int width, int height);
 void bdpt_host_free(void* p);
 const char* bdpt_host_last_error(void);
 #ifdef __cplusplus

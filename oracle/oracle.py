@@ -39,6 +39,7 @@ def lib():
         L.oracle_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.oracle_destroy.argtypes = [C.c_void_p]
         L.oracle_set_frame.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.oracle_set_cell.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         for name in ("oracle_intersect", "oracle_intersect_brute", "oracle_bsdf_eval", "oracle_bsdf_sample",
                      "oracle_light_eval", "oracle_camera_eval"):
             getattr(L, name).argtypes = [C.c_void_p, dp, C.c_long, dp]
@@ -82,6 +83,10 @@ class Oracle:
     def set_frame(self, w: int, h: int) -> None:
         lib().oracle_set_frame(self.h, w, h)
         self.W, self.H = w, h
+
+    def set_cell(self, x: int = 0, y: int = 0, dx: int = 0, dy: int = 0) -> None:
+        """Cell render (reference `-p x y dx dy`): only these pixels are sampled; dx = 0 restores the whole frame."""
+        lib().oracle_set_cell(self.h, x, y, dx, dy)
 
     def _batch(self, fn, arr, n_in, n_out):
         arr = np.ascontiguousarray(arr, np.float64).reshape(-1, n_in)

@@ -376,6 +376,31 @@ def test_ragged_frames_and_short_paths_match_oracle(api, O, name, W, H, ns, m):
     assert relmse(ge, oe) <= 2e-3 and relmse(gl, ol) <= 2e-3 and relmse(gs, os_) <= 2e-3
 
 
+def test_cell_render_matches_oracle(api, O):
+    """bdpt_set_cell (the reference's `-p x y dx dy`): only the cell's pixels are sampled — eye image zero outside it and
+    equal to the full render's inside; the light image is what THOSE samples' light subpaths splat, anywhere."""
+    name, W, H, ns, m = "CBspheres", 64, 48, 8, 4
+    x, y, dx, dy = 13, 9, 30, 21            # ragged against the 8x4 tiles
+    R = make_renderer(api, name, W, H, ns_aa=ns, max_ray_depth=m, seed=6)
+    R.set_cell(x, y, dx, dy)
+    R.render()
+    gs, ge, gl = (R.framebuffer(i).astype(np.float64) for i in range(3))
+    assert R.stats()["samples"] == dx * dy * ns
+    orc = O.Oracle(load_scene(name), W, H)
+    orc.set_cell(x, y, dx, dy)
+    os_, oe, ol, _ = orc.render(ns, m, rng_mode=1, seed=6, threads=8)
+    assert relmse(ge, oe) <= 1e-3 and relmse(gl, ol) <= 1e-3 and relmse(gs, os_) <= 1e-3
+    outside = np.ones((H, W), bool); outside[y:y + dy, x:x + dx] = False
+    assert np.all(ge[outside] == 0) and gl[outside].sum() > 0
+    F = make_renderer(api, name, W, H, ns_aa=ns, max_ray_depth=m, seed=6); F.render()
+    assert np.allclose(F.framebuffer(1)[y:y + dy, x:x + dx], ge[y:y + dy, x:x + dx], rtol=1e-6, atol=1e-7)
+    with pytest.raises(api.BdptError, match="cell"):
+        R.set_cell(50, 40, 30, 30)
+    R.set_cell()                             # back to the whole frame
+    R.clear(); R.render()
+    assert relmse(R.framebuffer(0), F.framebuffer(0)) <= 1e-9
+
+
 def test_image_does_not_depend_on_batching(api, monkeypatch):
     """The same frame rendered in 2^10-sample batches (hundreds of batches, the last one partial) and in one batch."""
     name, W, H, ns, m = "CBbunny", 61, 47, 5, 5

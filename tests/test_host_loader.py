@@ -177,3 +177,106 @@ def test_cli_renders_like_the_library(tmp_path):
     assert np.mean(np.abs(img.astype(int) - ref.astype(int)) <= 1) > 0.999
     rate = read_png(str(out)[:-4] + "_rate.png")
     assert (rate[..., 0] == 255).all() and (rate[..., 1:3] == 0).all()
+
+
+# ------------------------------------------------------------------ `-c <camera settings file>` and `-p <cell>`
+def read_png_any(path):
+    """RGBA8 array of any PNG (lodepng, which the reference writes with, drops an all-opaque alpha channel)."""
+    Image = pytest.importorskip("PIL.Image")
+    return np.asarray(Image.open(path).convert("RGBA"))
+
+
+def write_camera_settings(path, cam, pos=None, hfov=None, vfov=None):
+    """A file in Camera::dump_settings' format (reference camera.cpp:152-167) for the given flat-scene camera."""
+    c = cam[0]
+    c2w = np.array(c["c2w"]).reshape(3, 3).T          # columns -> c2w(row, col)
+    p = np.array(c["pos"]) if pos is None else np.array(pos, float)
+    r = lambda v: repr(float(v))
+    with open(path, "w") as f:
+        f.write(f"{r(c['hfov_deg'] if hfov is None else hfov)} {r(c['vfov_deg'] if vfov is None else vfov)} 1.3333 {r(c['nclip'])} {r(c['fclip'])}\n")
+        f.write(" ".join(r(v) for v in list(p) + list(c["target"])) + " \n")
+        f.write("0 0 5 0.1 100\n")
+        f.write(" ".join(r(v) for v in c2w.reshape(-1)) + " \n")
+        f.write(f"{r(c['screen_w'])} {r(c['screen_h'])} {r(c['screen_dist'])}\n")
+        f.write("4.56 0.0\n")
+
+
+def test_camera_settings_file_against_the_reference_binary(tmp_path):
+    """`-c file` (Camera::load_settings, camera.cpp:169-186) is pinned by the reference ITSELF: pathtracer_ref renders
+    CBspheres_lambertian with `-r 48 36 -c file` (a moved camera with its own fovs) on one thread; the fp64 oracle, given
+    the camera our parser produces for the same file, reproduces the PNG byte for byte (rng_mode 0 = the reference's
+    own random streams).  This also pins the ORDER: the file is applied after -r, its fovs win (main.cpp:174-178)."""
+    from bdpt import host
+    from oracle import oracle as O
+    dae = find_dae(CASES["CBspheres_lambertian"])
+    if dae is None or not os.path.exists(O.REF_CLI):
+        pytest.skip("needs the reference binary and its .dae inputs (oracle/_ref)")
+    sc = host.load_dae(dae)
+    W, H, ns, m = 48, 36, 2, 3
+    cfg = tmp_path / "cam.txt"
+    pos = np.array(sc.camera[0]["pos"]) + np.array([0.0, 0.0, -0.8])     # dolly in along the view axis (c2w unchanged)
+    write_camera_settings(cfg, sc.camera, pos=pos, hfov=40.0, vfov=31.0)
+    out = tmp_path / "ref.png"
+    subprocess.run([O.REF_CLI, "-t", "1", "-s", str(ns), "-m", str(m), "-r", str(W), str(H), "-c", str(cfg), "-f", str(out), dae],
+                   check=True, capture_output=True)
+    ref = read_png_any(str(out))
+    cam = host.apply_camera_settings(host.load_dae(dae, W, H), str(cfg), W, H)
+    assert cam.camera[0]["hfov_deg"] == 40.0 and cam.camera[0]["vfov_deg"] == 31.0 and np.allclose(cam.camera[0]["pos"], pos)
+    img = O.Oracle(cam, W, H).render(ns, m, rng_mode=0)[0]
+    px = (np.clip(np.power(np.maximum(img[::-1], 0) * np.sqrt(2.0), 1 / 2.2), 0, 1) * 255).astype(np.uint8)   # toColor + flip
+    assert ref.shape == (H, W, 4)
+    assert np.array_equal(ref[..., :3], px), "the oracle with the parsed camera reproduces the reference's -c render"
+    # and without -c the image is a different one
+    subprocess.run([O.REF_CLI, "-t", "1", "-s", str(ns), "-m", str(m), "-r", str(W), str(H), "-f", str(out), dae], check=True, capture_output=True)
+    assert not np.array_equal(read_png_any(str(out))[..., :3], px)
+
+
+def test_cell_render_against_the_reference_binary(tmp_path):
+    """`-p x y dx dy` (render_to_file's cell path, raytraced_renderer.cpp:338-346): the oracle with the same cell
+    reproduces the reference's cell PNG byte for byte — only the cell's pixels are sampled, the image is dx x dy."""
+    from bdpt import host
+    from oracle import oracle as O
+    dae = find_dae(CASES["CBspheres_lambertian"])
+    if dae is None or not os.path.exists(O.REF_CLI):
+        pytest.skip("needs the reference binary and its .dae inputs (oracle/_ref)")
+    W, H, ns, m = 48, 36, 2, 3
+    x, y, dx, dy = 10, 6, 20, 16
+    out = tmp_path / "cell.png"
+    subprocess.run([O.REF_CLI, "-t", "1", "-s", str(ns), "-m", str(m), "-r", str(W), str(H), "-p", str(x), str(y), str(dx), str(dy),
+                    "-f", str(out), dae], check=True, capture_output=True)
+    ref = read_png_any(str(out))
+    assert ref.shape == (dy, dx, 4)
+    orc = O.Oracle(host.load_dae(dae, W, H), W, H)
+    orc.set_cell(x, y, dx, dy)
+    img = orc.render(ns, m, rng_mode=0)[0]
+    px = (np.clip(np.power(np.maximum(img[::-1], 0) * np.sqrt(2.0), 1 / 2.2), 0, 1) * 255).astype(np.uint8)
+    assert np.array_equal(ref[..., :3], px[H - y - dy:H - y, x:x + dx])
+
+
+@pytest.mark.gpu
+def test_cli_camera_file_and_cell(tmp_path):
+    """`pathtracer -c file -p x y dx dy`: the CLI's image is the crop of what the library renders for the same camera."""
+    from bdpt import api, host
+    dae = find_dae(CASES["CBspheres"])
+    if dae is None:
+        pytest.skip("no .dae input on this box")
+    W, H, ns, m = 96, 72, 16, 4
+    x, y, dx, dy = 24, 10, 40, 32
+    sc = host.load_dae(dae)
+    cfg = tmp_path / "cam.txt"
+    write_camera_settings(cfg, sc.camera, pos=np.array(sc.camera[0]["pos"]) + np.array([0.3, 0.1, -0.5]), hfov=45.0, vfov=35.0)
+    exe = os.path.join(ROOT, "bidirectional-pathtracing_b200", "host", "pathtracer")
+    out = tmp_path / "cell.png"
+    r = subprocess.run([exe, "-s", str(ns), "-m", str(m), "-r", str(W), str(H), "-c", str(cfg), "-p", str(x), str(y), str(dx), str(dy),
+                        "-f", str(out), dae], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Cell job completed" in r.stdout
+    img = read_png(str(out))
+    assert img.shape == (dy, dx, 4)
+    cam = host.apply_camera_settings(host.load_dae(dae, W, H), str(cfg), W, H)
+    R = api.Renderer(0, ns_aa=ns, max_ray_depth=m, seed=0)
+    R.set_scene(cam); R.set_frame_size(W, H); R.set_cell(x, y, dx, dy); R.render()
+    ref = R.tonemap(0)[H - y - dy:H - y, x:x + dx]
+    assert np.mean(np.abs(img.astype(int) - ref.astype(int)) <= 1) > 0.999
+    rate = read_png(str(out)[:-4] + "_rate.png")
+    assert rate.shape == (H, W, 4) and (rate[H - y - 1, x, :3] == [255, 0, 0]).all() and (rate[0, 0, :3] == [0, 0, 255]).all()
