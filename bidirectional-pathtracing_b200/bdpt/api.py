@@ -50,7 +50,7 @@ class Stats(C.Structure):
 
 
 EXPORTS = ["bdpt_create", "bdpt_destroy", "bdpt_last_error", "bdpt_set_stream", "bdpt_upload_scene",
-           "bdpt_set_camera", "bdpt_set_frame", "bdpt_set_cell", "bdpt_clear", "bdpt_render", "bdpt_read_framebuffer",
+           "bdpt_set_camera", "bdpt_set_environment_map", "bdpt_set_frame", "bdpt_set_cell", "bdpt_clear", "bdpt_render", "bdpt_read_framebuffer",
            "bdpt_framebuffer_device", "bdpt_tonemap_rgba8", "bdpt_get_stats", "bdpt_intersect_batch",
            "bdpt_occluded_batch", "bdpt_bsdf_eval_batch", "bdpt_bsdf_sample_batch", "bdpt_light_eval_batch",
            "bdpt_camera_eval_batch", "bdpt_trace_sample", "bdpt_host_build_bvh", "bdpt_device_bvh",
@@ -76,6 +76,7 @@ def load_library():
     L.bdpt_set_stream.argtypes = [vp, vp]
     L.bdpt_upload_scene.argtypes = [vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32]
     L.bdpt_set_camera.argtypes = [vp, vp]
+    L.bdpt_set_environment_map.argtypes = [vp, vp, C.c_int, C.c_int]
     L.bdpt_set_frame.argtypes = [vp, C.c_int, C.c_int]
     L.bdpt_set_cell.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
     L.bdpt_clear.argtypes = [vp]
@@ -163,6 +164,14 @@ class Renderer:
     def set_camera(self, camera: np.ndarray):
         cam = np.ascontiguousarray(camera)
         self._ck(self.L.bdpt_set_camera(self.h, cam.ctypes.data))
+
+    def set_environment_map(self, rgb):
+        """Lat-long radiance map (h, w, 3) float32 of the scene's environment light, row 0 = up; None: constant."""
+        if rgb is None:
+            self._ck(self.L.bdpt_set_environment_map(self.h, None, 0, 0))
+            return
+        a = np.ascontiguousarray(rgb, np.float32)
+        self._ck(self.L.bdpt_set_environment_map(self.h, a.ctypes.data, a.shape[1], a.shape[0]))
 
     def set_frame_size(self, width: int, height: int):
         self._ck(self.L.bdpt_set_frame(self.h, width, height))

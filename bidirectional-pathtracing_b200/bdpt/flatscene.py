@@ -16,7 +16,7 @@ import numpy as np
 MAGIC = 0x3130534654504442  # "BDPTFS01"
 
 MAT_DIFFUSE, MAT_EMISSION, MAT_MIRROR, MAT_GLASS, MAT_REFRACTION, MAT_MICROFACET = range(6)
-LIGHT_AREA, LIGHT_POINT = 0, 1
+LIGHT_AREA, LIGHT_POINT, LIGHT_ENV = 0, 1, 2
 PRIM_TRIANGLE, PRIM_SPHERE = 0, 1
 
 HEADER_DT = np.dtype([("magic", "<u8"), ("n_prims", "<u4"), ("n_materials", "<u4"),

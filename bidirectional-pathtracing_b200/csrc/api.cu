@@ -38,6 +38,7 @@ struct BdptContext {
   size_t cap_scene[6] = {0, 0, 0, 0, 0, 0};
   uint32_t bvh_nodes = 0, bvh_depth = 0;
   double ms_bvh_build = 0;
+  float4* d_envmap = nullptr; int env_w = 0, env_h = 0;   // lat-long map of the environment light (bdpt_set_environment_map)
   // device build (bvh_gpu.cuh): workspace (grow-only), pinned counters, the leaf order it produced
   char* bvh_ws = nullptr; size_t bvh_ws_bytes = 0;
   unsigned int* h_bvh = nullptr;
@@ -515,7 +516,7 @@ void bdpt_destroy(BdptContext* ctx) {
   dfree(ctx->slab); dfree(ctx->counters); ctx->qctr = nullptr; ctx->d_stats = nullptr;
   if (ctx->h_qctr) cudaFreeHost(ctx->h_qctr);
   if (ctx->h_bvh) cudaFreeHost(ctx->h_bvh);
-  dfree(ctx->bvh_ws);
+  dfree(ctx->bvh_ws); dfree(ctx->d_envmap);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -539,7 +540,7 @@ int bdpt_upload_scene(BdptContext* ctx, const BdptCamera* camera, const BdptMate
   CK(cudaSetDevice(ctx->device));
   if (n_lights == 0) return fail(ctx, BDPT_ERR_SCENE, "scene has no light: BDPT needs at least one (bidirection.cpp:109)");
   for (uint32_t i = 0; i < n_lights; i++)
-    if (lights[i].type != BDPT_LIGHT_AREA && lights[i].type != BDPT_LIGHT_POINT)
+    if (lights[i].type != BDPT_LIGHT_AREA && lights[i].type != BDPT_LIGHT_POINT && lights[i].type != BDPT_LIGHT_ENV)
       return fail(ctx, BDPT_ERR_SCENE, "light type not supported by BDPT (only area and point lights implement sample_Le, light.cpp)");
   for (uint32_t i = 0; i < n_materials; i++)
     if (materials[i].type < BDPT_MAT_DIFFUSE || materials[i].type > BDPT_MAT_MICROFACET)
@@ -560,7 +561,10 @@ int bdpt_upload_scene(BdptContext* ctx, const BdptCamera* camera, const BdptMate
     if (e == cudaSuccess) *cap = bytes;
     return e;
   };
-  std::vector<float4> hm(5 * (size_t)std::max<uint32_t>(n_materials, 1));
+  // (one extra material: the emitter the environment's sphere carries, index n_materials)
+  std::vector<float4> hm(5 * ((size_t)n_materials + 1), make_float4(0.f, 0.f, 0.f, 0.f));
+  hm[5 * (size_t)n_materials + 0] = make_float4(0.f, 0.f, 0.f, ibits(BDPT_MAT_EMISSION));
+  hm[5 * (size_t)n_materials + 2] = make_float4(1.f, 1.f, 1.f, 0.f);
   for (uint32_t i = 0; i < n_materials; i++) {
     const BdptMaterial& m = materials[i];
     hm[5 * i + 0] = make_float4((float)m.reflectance[0], (float)m.reflectance[1], (float)m.reflectance[2], ibits(m.type));
@@ -570,8 +574,29 @@ int bdpt_upload_scene(BdptContext* ctx, const BdptCamera* camera, const BdptMate
     hm[5 * i + 4] = make_float4((float)m.k[0], (float)m.k[1], (float)m.k[2], 0.f);
   }
   std::vector<float4> hl(5 * (size_t)n_lights);
+  int env_light = -1;
   for (uint32_t i = 0; i < n_lights; i++) {
     const BdptLight& l = lights[i];
+    if (l.type == BDPT_LIGHT_ENV) {
+      // the far sphere sits around the scene's bounding sphere (centre and half diagonal of the primitives' box)
+      double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+      for (uint32_t k = 0; k < n_prims; k++) {
+        const double* d = prims[k].data;
+        const int nv = prims[k].type == BDPT_PRIM_TRIANGLE ? 3 : 1;
+        const double r = prims[k].type == BDPT_PRIM_TRIANGLE ? 0.0 : d[3];
+        for (int v = 0; v < nv; v++) for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], d[3 * v + a] - r); hi[a] = std::max(hi[a], d[3 * v + a] + r); }
+      }
+      if (n_prims == 0) for (int a = 0; a < 3; a++) { lo[a] = -1; hi[a] = 1; }
+      const double dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+      const double rs = std::max(1e-6, 0.5 * std::sqrt(dx * dx + dy * dy + dz * dz)), R = 1000.0 * rs;
+      hl[5 * i + 0] = make_float4((float)l.radiance[0], (float)l.radiance[1], (float)l.radiance[2], ibits(l.type));
+      hl[5 * i + 1] = make_float4((float)(0.5 * (lo[0] + hi[0])), (float)(0.5 * (lo[1] + hi[1])), (float)(0.5 * (lo[2] + hi[2])), (float)(4.0 * 3.14159265358979323 * R * R));
+      hl[5 * i + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+      hl[5 * i + 3] = make_float4((float)R, (float)rs, 0.f, 0.f);
+      hl[5 * i + 4] = make_float4(0.f, 0.f, 0.f, 0.f);
+      env_light = (int)i;
+      continue;
+    }
     double nx = std::sqrt(l.dim_x[0] * l.dim_x[0] + l.dim_x[1] * l.dim_x[1] + l.dim_x[2] * l.dim_x[2]);
     double ny = std::sqrt(l.dim_y[0] * l.dim_y[0] + l.dim_y[1] * l.dim_y[1] + l.dim_y[2] * l.dim_y[2]);
     hl[5 * i + 0] = make_float4((float)l.radiance[0], (float)l.radiance[1], (float)l.radiance[2], ibits(l.type));
@@ -645,6 +670,8 @@ int bdpt_upload_scene(BdptContext* ctx, const BdptCamera* camera, const BdptMate
   ctx->sc.nodes = ctx->d_nodes; ctx->sc.prims = ctx->d_prims; ctx->sc.shading = ctx->d_shading; ctx->sc.prims64 = ctx->d_prims64;
   ctx->sc.materials = ctx->d_mats; ctx->sc.lights = ctx->d_lights;
   ctx->sc.n_lights = (int)n_lights; ctx->sc.n_materials = (int)n_materials;
+  ctx->sc.env_light = env_light;
+  ctx->sc.envmap = ctx->d_envmap; ctx->sc.env_w = ctx->env_w; ctx->sc.env_h = ctx->env_h;
   ctx->sc.qbias_bits = 0x47000000u;
   ctx->sc.n_nodes = (int)n_nodes; ctx->sc.n_prims = (int)n_prims;
   ctx->bvh_nodes = n_nodes; ctx->bvh_depth = depth;
@@ -664,6 +691,22 @@ int bdpt_upload_scene(BdptContext* ctx, const BdptCamera* camera, const BdptMate
   ctx->cam_base = *camera;
   ctx->have_scene = true;
   if (ctx->W > 0) make_dcamera(ctx->cam_base, ctx->W, ctx->H, &ctx->cam);
+  return BDPT_OK;
+}
+
+int bdpt_set_environment_map(BdptContext* ctx, const float* rgb, int width, int height) {
+  if (!ctx || ((width > 0 || height > 0) && (!rgb || width <= 0 || height < 2))) return BDPT_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  dfree(ctx->d_envmap); ctx->env_w = ctx->env_h = 0;
+  if (width > 0) {
+    std::vector<float4> h((size_t)width * height);
+    for (size_t i = 0; i < h.size(); i++) h[i] = make_float4(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], 0.f);
+    CK(cudaMalloc(&ctx->d_envmap, h.size() * sizeof(float4)));
+    CK(cudaMemcpy(ctx->d_envmap, h.data(), h.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    ctx->env_w = width; ctx->env_h = height;
+  }
+  ctx->sc.envmap = ctx->d_envmap; ctx->sc.env_w = ctx->env_w; ctx->sc.env_h = ctx->env_h;
   return BDPT_OK;
 }
 

@@ -65,12 +65,13 @@ struct DMaterial {
   float4 q[5];
 };
 
-// Light record: 6 x float4.
+// Light record: 5 x float4.
 //   q0 = {radiance.rgb, as_float(type)}
 //   q1 = {position.xyz, area}
 //   q2 = {direction.xyz (unit, as stored by the loader), 0}
 //   q3 = {dim_x.xyz, 0}
 //   q4 = {dim_y.xyz, 0}
+// environment (BDPT_LIGHT_ENV): q1 = {centre of the far sphere, its area 4 pi R^2}, q3 = {R, scene bounding radius, 0, 0}
 struct DLight {
   float4 q[5];
 };
@@ -103,6 +104,9 @@ struct DScene {
   const double* prims64;    // leaf-ordered fp64 geometry, 10 doubles each: triangle p1 p2 p3 (+pad) / sphere c, r
   const float4* materials;  // DMaterial as 5 x float4
   const float4* lights;     // DLight as 5 x float4
+  const float4* envmap;     // lat-long radiance map of the environment light (row 0 = up) or null: constant
+  int env_w, env_h;
+  int env_light;            // index of the environment light, -1 = none; its sphere carries material n_materials
   int n_lights;
   int n_materials;
   int n_nodes;

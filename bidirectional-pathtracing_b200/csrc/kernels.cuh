@@ -146,7 +146,7 @@ __device__ inline bool walk_begin(const Job& J, unsigned i, WalkState& W, Trav& 
     int li = W.rng.pick(J.sc.n_lights);
     Light L = load_light(J.sc, li);
     float pA, pdir; f3 nl;
-    f3 Le = light_sample_Le(L, W.rng, &o, &d, &pA, &pdir, &nl);
+    f3 Le = light_sample_Le(J.sc, L, W.rng, &o, &d, &pA, &pdir, &nl);
     pA /= (float)J.sc.n_lights;
     W.prev_n = nl; W.alpha = Le * (1.0f / pA); W.prev_pdf = pdir;
     W.pdfeval_prev = pdir; W.D_prev = pA; W.S_prev = 1.f;
@@ -166,8 +166,29 @@ __device__ inline bool walk_begin(const Job& J, unsigned i, WalkState& W, Trav& 
 template <int TR = 0>
 __device__ inline bool walk_shade(const Job& J, WalkState& W, Trav& T) {
   const DScene& sc = J.sc;
-  if (T.hit.leaf < 0) return false;
   const f3 o = T.o, d = T.d;
+  if (T.hit.leaf < 0) {
+    if (sc.env_light < 0) return false;
+    // The ray leaves the scene: it meets the environment's sphere (shading.cuh, "environment light"), whose surface
+    // is an emitter — the vertex is stored like any other emissive end of a subpath, and the walk ends there.
+    const Light L = load_light(sc, sc.env_light);
+    const f3 oc = o - L.position;
+    const float b = dot(oc, d), cc = norm2(oc) - L.dim_x.x * L.dim_x.x;
+    if (cc >= 0.f) return false;
+    const float te = -b + sqrtf(b * b - cc);
+    const f3 pe = o + d * te, ne = normalized(L.position - pe);
+    const float cos_prev = fabsf(dot(W.prev_n, d));
+    const float ge = cos_prev * fabsf(dot(ne, d)) / (te * te);
+    W.alpha = W.alpha * W.prev_f * (cos_prev / W.prev_pdf);
+    const float D_e = (W.kind == 0 && W.j == 2) ? 1.f : W.pdfeval_prev * ge;
+    float S_e = W.delta_prev ? 0.f : 1.f;
+    if (W.S_prev > 0.f) S_e += mis_pow(J, cosine_pdf(-dot(ne, d)) * ge / W.D_prev) * W.S_prev;
+    store_vertex(J, VSLOT(J, W.kind, W.j, W.si), make_float4(pe.x, pe.y, pe.z, __int_as_float(sc.n_materials)),
+                 make_float4(ne.x, ne.y, ne.z, D_e), make_float4(W.alpha.x, W.alpha.y, W.alpha.z, clampS(S_e)),
+                 make_float4(-d.x, -d.y, -d.z, 1.f));
+    W.nv = W.j; W.emis = true;
+    return false;
+  }
   f3 n, hit_p; int prim, mat;
   finish_hit<TR>(sc, T.hit, o, d, &n, &prim, &mat, &hit_p);
   const float t = T.hit.t;
@@ -400,7 +421,7 @@ __global__ void __launch_bounds__(BDPT_CONNECT_NT, MINB) k_connect(const Job J) 
             if (light_contain_point(L, E.pos)) { lj = i; break; }
           }
           if (lj < 0) c = zero;
-          else { float pp, dp; c = light_sample_pdf(L, E.pos, -E.wo, &pp, &dp); }
+          else { float pp, dp; c = light_sample_pdf(sc, L, E.pos, -E.wo, &pp, &dp); }
         }
         contrib = E.alpha * c;
         if (norm(contrib) > BDPT_EPS_F && lj >= 0) {
@@ -413,7 +434,7 @@ __global__ void __launch_bounds__(BDPT_CONNECT_NT, MINB) k_connect(const Job J) 
             delta_prev = type_is_delta(mat_type<TR>(sc, P.mat));
             if (P.S > 0.f) {
               float pp, dp;
-              light_sample_pdf(L, E.pos, -E.wo, &pp, &dp);  // dir pdf of leaving the light toward e_{t-1}
+              light_sample_pdf(sc, L, E.pos, -E.wo, &pp, &dp);  // dir pdf of leaving the light toward e_{t-1}
               f3 wv = P.pos - E.pos; float d2 = dot(wv, wv);
               f3 wd = wv * rsqrtf(d2);
               float gp = fabsf(dot(E.n, wd) * dot(wd, P.n)) / d2;
@@ -435,7 +456,7 @@ __global__ void __launch_bounds__(BDPT_CONNECT_NT, MINB) k_connect(const Job J) 
           int li = rng.pick(sc.n_lights);
           Light L = load_light(sc, li);
           float pA;
-          f3 rad = light_sample_Le_point(L, E.pos, rng, &Lv.pos, &pA, &ls_dir_pdf, &Lv.n);
+          f3 rad = light_sample_Le_point(sc, L, E.pos, rng, &Lv.pos, &pA, &ls_dir_pdf, &Lv.n);
           pA /= (float)sc.n_lights;
           Lv.alpha = rad * (1.0f / pA);
           Lv.mat = -1; Lv.q = 1.f; Lv.D = pA; Lv.S = 1.f; Lv.wo = zero;
@@ -803,7 +824,7 @@ __global__ void k_light_eval(DScene sc, const float* in, size_t n, float* out) {
   f3 p = mk3(q[1], q[2], q[3]), wi = mk3(q[4], q[5], q[6]);
   float pp = 0.f, dp = 0.f;
   o[0] = light_contain_point(L, p) ? 1.f : 0.f;
-  f3 le = light_sample_pdf(L, p, wi, &pp, &dp);
+  f3 le = light_sample_pdf(sc, L, p, wi, &pp, &dp);
   o[1] = le.x; o[2] = le.y; o[3] = le.z; o[4] = pp; o[5] = dp;
 }
 

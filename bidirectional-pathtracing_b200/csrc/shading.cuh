@@ -284,9 +284,39 @@ __device__ inline f3 bsdf_sample_f(const Mat& m, f3 wo, f3* wi, float* pdf, RNG&
 // ------------------------------------------------------------------ lights
 struct Light {
   int type;
-  f3 radiance, position, direction, dim_x, dim_y;
+  f3 radiance, position, direction, dim_x, dim_y;   // environment: position = centre, dim_x = {R, scene radius, -}
   float area;
 };
+
+// ---- environment light: an extension (the reference's EnvironmentLight aborts in every method BDPT calls,
+// environment_light.cpp:182-208).  Defined in oracle/bdpt_oracle.cpp ("environment"): a sphere of radius R = 1000 x
+// the scene's bounding radius around the scene's centre that emits inward — an area light like any other for every
+// formula of the path.  Radiance toward the scene from sphere point c + R u = radiance * map(u), the map looked up
+// like EnvironmentLight::sample_dir does (dir -> theta, phi -> x, y -> bilerp, :83-136,157-165).
+__device__ inline f3 env_map_lookup(const DScene& sc, f3 dir) {
+  if (!sc.envmap) return mk3(1.f);
+  const int w = sc.env_w, h = sc.env_h;
+  const f3 u = normalized(dir);
+  const float theta = acosf(fminf(fmaxf(u.y, -1.f), 1.f));
+  const float phi = atan2f(-u.z, u.x) + BDPT_PI;
+  const float x = phi * (0.5f * BDPT_INV_PI) * (float)w, y = theta * BDPT_INV_PI * (float)h;
+  int right = (int)lroundf(x), left, v = (int)lroundf(y);
+  const float u1 = (float)right - x + .5f;
+  float v1;
+  if (right == 0 || right == w) { left = w - 1; right = 0; } else left = right - 1;
+  if (v == 0) { v = 1; v1 = 1.f; } else if (v == h) { v = h - 1; v1 = 0.f; } else v1 = (float)v - y + .5f;
+  const int bottom = w * v, top = bottom - w;
+  const float u0 = 1.f - u1;
+  const float4 tl = __ldg(sc.envmap + top + left), tr = __ldg(sc.envmap + top + right);
+  const float4 bl = __ldg(sc.envmap + bottom + left), br = __ldg(sc.envmap + bottom + right);
+  return (mk3(tl.x, tl.y, tl.z) * u1 + mk3(tr.x, tr.y, tr.z) * u0) * v1 + (mk3(bl.x, bl.y, bl.z) * u1 + mk3(br.x, br.y, br.z) * u0) * (1.f - v1);
+}
+__device__ inline f3 env_radiance(const DScene& sc, const Light& l, f3 dir_from_centre) { return l.radiance * env_map_lookup(sc, dir_from_centre); }
+// emission direction density at a sphere point (solid angle): the directions that reach the scene's bounding disk
+__device__ inline float env_dir_pdf(const Light& l, float cos_at_sphere) {
+  const float R = l.dim_x.x, rs = l.dim_x.y;
+  return cos_at_sphere > 0.f ? R * R * cos_at_sphere / (BDPT_PI * rs * rs) : 0.f;
+}
 
 __device__ inline Light load_light(const DScene& sc, int i) {
   const float4* p = sc.lights + 5 * i;
@@ -301,6 +331,7 @@ __device__ inline Light load_light(const DScene& sc, int i) {
 
 // AreaLight::contain_point light.cpp:257-262 (a plane test only); PointLight :136-139
 __device__ inline bool light_contain_point(const Light& l, f3 p) {
+  if (l.type == BDPT_LIGHT_ENV) return fabsf(norm(p - l.position) - l.dim_x.x) < 1e-3f * l.dim_x.x;
   if (l.type == BDPT_LIGHT_AREA) {
     f3 d = normalized(l.position - p);
     return fabsf(dot(d, l.direction)) < BDPT_EPS_F;
@@ -310,9 +341,15 @@ __device__ inline bool light_contain_point(const Light& l, f3 p) {
 
 // AreaLight::sample_pdf light.cpp:264-284; PointLight::sample_pdf :141-151.
 // wi points TOWARD the light (world space).  Returns Le.
-__device__ inline f3 light_sample_pdf(const Light& l, f3 p, f3 wi, float* point_pdf, float* dir_pdf) {
+__device__ inline f3 light_sample_pdf(const DScene& sc, const Light& l, f3 p, f3 wi, float* point_pdf, float* dir_pdf) {
   if (!light_contain_point(l, p)) { *point_pdf = 0.f; *dir_pdf = 0.f; return mk3(0.f); }
   if (l.type == BDPT_LIGHT_POINT) { *point_pdf = 1.f; *dir_pdf = 0.25f * BDPT_INV_PI; return l.radiance; }
+  if (l.type == BDPT_LIGHT_ENV) {
+    const f3 u = normalized(p - l.position);       // outward; the sphere emits along -u, wi points TOWARD the light
+    *point_pdf = 1.0f / l.area;
+    *dir_pdf = env_dir_pdf(l, is_zero(wi) ? 1.f : dot(u, normalized(wi)));
+    return *dir_pdf > 0.f ? env_radiance(sc, l, u) : mk3(0.f);
+  }
   *point_pdf = 1.0f / l.area;
   // local z of normalize(w2o * (-wi)); w2o's z row is the unit light direction
   f3 zdir = normalized(l.direction);
@@ -322,12 +359,28 @@ __device__ inline f3 light_sample_pdf(const Light& l, f3 p, f3 wi, float* point_
 }
 
 // AreaLight::sample_Le light.cpp:219-232; PointLight::sample_Le :115-123
-__device__ inline f3 light_sample_Le(const Light& l, Rng& rng, f3* o, f3* d, float* point_pdf, float* dir_pdf, f3* normal) {
+__device__ inline f3 light_sample_Le(const DScene& sc, const Light& l, Rng& rng, f3* o, f3* d, float* point_pdf, float* dir_pdf, f3* normal) {
   if (l.type == BDPT_LIGHT_POINT) {
     float u1 = rng.uniform(), u2 = rng.uniform();
     *o = l.position; *d = uniform_sphere(u1, u2);
     *point_pdf = 1.f; *dir_pdf = 0.25f * BDPT_INV_PI; *normal = *d;
     return l.radiance;
+  }
+  if (l.type == BDPT_LIGHT_ENV) {
+    // a uniform direction of travel, a uniform point of the scene's bounding disk perpendicular to it, carried back
+    // onto the sphere
+    const float u1 = rng.uniform(), u2 = rng.uniform(), u3 = rng.uniform(), u4 = rng.uniform();
+    const f3 dd = uniform_sphere(u1, u2);
+    const Frame fr = make_frame(dd);
+    float sn, cs;
+    sincos_2pi(u4, &sn, &cs);
+    const float rr = l.dim_x.y * sqrtf(u3);
+    const f3 p0 = (l.position - dd * l.dim_x.x) + fr.x * (rr * cs) + fr.y * (rr * sn);
+    const f3 u = normalized(p0 - l.position);
+    *o = l.position + u * l.dim_x.x; *d = dd; *normal = -u;
+    *point_pdf = 1.0f / l.area;
+    *dir_pdf = env_dir_pdf(l, -dot(u, dd));
+    return env_radiance(sc, l, u);
   }
   float sx = rng.uniform() - 0.5f, sy = rng.uniform() - 0.5f;
   *o = l.position + sx * l.dim_x + sy * l.dim_y;
@@ -341,12 +394,21 @@ __device__ inline f3 light_sample_Le(const Light& l, Rng& rng, f3* o, f3* d, flo
 }
 
 // AreaLight::sample_Le_point light.cpp:234-255; PointLight::sample_Le_point :125-134
-__device__ inline f3 light_sample_Le_point(const Light& l, f3 p, Rng& rng, f3* point, float* point_pdf, float* dir_pdf,
+__device__ inline f3 light_sample_Le_point(const DScene& sc, const Light& l, f3 p, Rng& rng, f3* point, float* point_pdf, float* dir_pdf,
                                            f3* normal) {
   if (l.type == BDPT_LIGHT_POINT) {
     f3 wi = normalized(l.position - p);
     *point = l.position; *point_pdf = 1.f; *dir_pdf = 0.25f * BDPT_INV_PI; *normal = -wi;
     return l.radiance;
+  }
+  if (l.type == BDPT_LIGHT_ENV) {
+    const float u1 = rng.uniform(), u2 = rng.uniform();
+    const f3 u = uniform_sphere(u1, u2);           // a uniform point of the sphere
+    *point = l.position + u * l.dim_x.x;
+    const f3 wi = normalized(*point - p);
+    *point_pdf = 1.0f / l.area; *normal = -u;
+    *dir_pdf = env_dir_pdf(l, dot(u, wi));
+    return *dir_pdf > 0.f ? env_radiance(sc, l, u) : mk3(0.f);
   }
   float sx = rng.uniform() - 0.5f, sy = rng.uniform() - 0.5f;
   *point = l.position + sx * l.dim_x + sy * l.dim_y;
@@ -386,6 +448,9 @@ __device__ inline float camera_sample_ray_pdf(const DCamera& c, f3 p, f3* wi, fl
   // C truncation toward zero, as the reference's double -> int conversion (camera.cpp:242-243)
   *px = (fx > -2.0e9f && fx < 2.0e9f) ? __float2int_rz(fx) : -1;
   *py = (fy > -2.0e9f && fy < 2.0e9f) ? __float2int_rz(fy) : -1;
+  // A point BEHIND the pinhole has no raster position (the reference divides by wc.z whatever its sign and would
+  // splat its mirror image; nothing in its scenes lies behind the camera, the environment's sphere does)
+  if (!(wc.z > 0.f)) { *px = -1; *py = -1; }
   return We;
 }
 

@@ -93,6 +93,12 @@ int bdpt_set_stream(BdptContext* ctx, void* cuda_stream);
 int bdpt_upload_scene(BdptContext* ctx, const BdptCamera* camera, const BdptMaterial* materials, uint32_t n_materials,
                       const BdptLight* lights, uint32_t n_lights, const BdptPrim* prims, uint32_t n_prims);
 int bdpt_set_camera(BdptContext* ctx, const BdptCamera* camera);
+/* Lat-long radiance map of the scene's environment light (BDPT_LIGHT_ENV in the light table, the reference's `-e`
+ * option: src/application/main.cpp:115-118, EnvironmentLight, src/scene/environment_light.cpp), width x height RGB
+ * floats, row 0 = straight up, looked up like EnvironmentLight::sample_dir (:157-165).  The light's `radiance` scales
+ * it; width = 0 removes the map (constant environment).  Independent of bdpt_upload_scene; the reference's BDPT aborts
+ * on environment lights (:182-208) — see bdpt_flatscene.h for what is defined here instead. */
+int bdpt_set_environment_map(BdptContext* ctx, const float* rgb, int width, int height);
 /* Applies Camera::set_screen_size semantics (camera.cpp:83-89) and (re)allocates the frame buffers. */
 int bdpt_set_frame(BdptContext* ctx, int width, int height);
 

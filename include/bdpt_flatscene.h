@@ -38,7 +38,12 @@ enum BdptMaterialType {
 
 enum BdptLightType {
   BDPT_LIGHT_AREA = 0,  /* AreaLight  light.cpp:199-284 */
-  BDPT_LIGHT_POINT = 1  /* PointLight light.cpp:102-153 */
+  BDPT_LIGHT_POINT = 1, /* PointLight light.cpp:102-153 */
+  /* EnvironmentLight (src/scene/environment_light.cpp), which the reference's BDPT aborts on (:182-208).
+   * Extension defined here: a far sphere that emits inward, radius 1000 x the scene's bounding radius about its
+   * centre — i.e. an ordinary area light for every formula of the path (bdpt_oracle.cpp "environment").  `radiance`
+   * is the constant radiance, or the scale of the lat-long map given with bdpt_set_environment_map. */
+  BDPT_LIGHT_ENV = 2
 };
 
 enum BdptPrimType { BDPT_PRIM_TRIANGLE = 0, BDPT_PRIM_SPHERE = 1 };

@@ -40,6 +40,7 @@ def lib():
         L.oracle_destroy.argtypes = [C.c_void_p]
         L.oracle_set_frame.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.oracle_set_cell.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.oracle_set_envmap.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         for name in ("oracle_intersect", "oracle_intersect_brute", "oracle_bsdf_eval", "oracle_bsdf_sample",
                      "oracle_light_eval", "oracle_camera_eval"):
             getattr(L, name).argtypes = [C.c_void_p, dp, C.c_long, dp]
@@ -83,6 +84,21 @@ class Oracle:
     def set_frame(self, w: int, h: int) -> None:
         lib().oracle_set_frame(self.h, w, h)
         self.W, self.H = w, h
+
+    def set_envmap(self, rgb) -> None:
+        """Lat-long radiance map (h, w, 3) float32 of the environment light, row 0 = up; None removes it."""
+        if rgb is None:
+            lib().oracle_set_envmap(self.h, None, 0, 0)
+            return
+        self._env = np.ascontiguousarray(rgb, np.float32)
+        lib().oracle_set_envmap(self.h, self._env.ctypes.data, self._env.shape[1], self._env.shape[0])
+
+    def envmap_lookup(self, dirs):
+        dirs = np.ascontiguousarray(dirs, np.float64).reshape(-1, 3)
+        out = np.empty_like(dirs)
+        lib().oracle_envmap_lookup.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_long, C.POINTER(C.c_double)]
+        lib().oracle_envmap_lookup(self.h, _dp(dirs), dirs.shape[0], _dp(out))
+        return out
 
     def set_cell(self, x: int = 0, y: int = 0, dx: int = 0, dy: int = 0) -> None:
         """Cell render (reference `-p x y dx dy`): only these pixels are sampled; dx = 0 restores the whole frame."""

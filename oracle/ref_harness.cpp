@@ -21,6 +21,10 @@
 //       in order from this fresh process, so the draws are the reference's default-seeded streams
 //       (random_util.h:10-22).  wi and pdf are preset to NaN: RefractionBSDF::sample_f returns
 //       without writing them on total internal reflection (advanced_bsdf.cpp:166-168).
+//   envdir    W H map.bin dirs.bin out.bin
+//       map: W x H x 3 fp64 radiance (row 0 = up); dirs: N x 3; out: N x 3 = EnvironmentLight::sample_dir
+//       (environment_light.cpp:157-165: dir -> theta, phi -> x, y -> bilerp) of a reference EnvironmentLight built
+//       on that map.  (Its constructor writes probability_debug.png into the working directory.)
 //   light     scene.dae in.bin out.bin
 //       in: N x {light, p[3], wi[3]} (7 each); out: N x {contain_point, Le[3] (sample_pdf), point_pdf, dir_pdf}
 //   camera    scene.dae W H in.bin out.bin
@@ -60,6 +64,7 @@
 #include "pathtracer/bidirection.h"
 #include "pathtracer/raytraced_renderer.h"
 #include "scene/collada/collada.h"
+#include "scene/environment_light.h"
 #include "scene/light.h"
 #include "scene/sphere.h"
 #include "scene/triangle.h"
@@ -272,6 +277,23 @@ int cmd_bsdf_sample(int argc, char** argv) {
   return 0;
 }
 
+int cmd_envdir(int argc, char** argv) {
+  size_t W = atoi(argv[2]), H = atoi(argv[3]);
+  std::vector<double> m = read_doubles(argv[4]);
+  HDRImageBuffer* img = new HDRImageBuffer(W, H);
+  for (size_t i = 0; i < W * H; i++) img->data[i] = Vector3D(m[3 * i], m[3 * i + 1], m[3 * i + 2]);
+  EnvironmentLight* env = new EnvironmentLight(img);
+  std::vector<double> in = read_doubles(argv[5]);
+  size_t n = in.size() / 3;
+  std::vector<double> out(n * 3);
+  for (size_t i = 0; i < n; i++) {
+    Ray r(Vector3D(0, 0, 0), Vector3D(in[3 * i], in[3 * i + 1], in[3 * i + 2]));
+    put3(&out[3 * i], env->sample_dir(r));
+  }
+  write_doubles(argv[6], out);
+  return 0;
+}
+
 int cmd_light(int argc, char** argv) {
   Loaded L = load_scene(argv[2], 0, 0, 1, 1, 1);
   std::vector<double> in = read_doubles(argv[3]);
@@ -384,6 +406,7 @@ int main(int argc, char** argv) {
   if (c == "intersect" && argc >= 5) return cmd_intersect(argc, argv);
   if (c == "bsdf" && argc >= 5) return cmd_bsdf(argc, argv);
   if (c == "bsdf_sample" && argc >= 5) return cmd_bsdf_sample(argc, argv);
+  if (c == "envdir" && argc >= 7) return cmd_envdir(argc, argv);
   if (c == "light" && argc >= 5) return cmd_light(argc, argv);
   if (c == "camera" && argc >= 7) return cmd_camera(argc, argv);
   if (c == "render" && argc >= 9) return cmd_render(argc, argv);

@@ -44,3 +44,26 @@ def load_scene(name):
 
 ALL_SCENES = ["CBspheres_lambertian", "CBspheres", "CBgems", "CBspheres_lambertian_occluded", "CBempty",
               "CBbunny", "CBcoil"]
+
+
+def env_scene(kind="sphere", radiance=(1.0, 1.0, 1.0)):
+    """Scenes with an environment light (BDPT_LIGHT_ENV; the reference's BDPT aborts on it: an extension, see
+    include/bdpt_flatscene.h).  "sphere": ONE diffuse sphere (rho = 0.8) alone under the environment — convex, so the
+    radiance it reflects under a constant environment L is exactly rho * L; "cornell": CBspheres with the environment
+    added to its area light.  The camera's screen distance is shortened so that a 48 x 36 frame sees what 480 x 360
+    does (the field of view depends on the resolution)."""
+    from bdpt import flatscene as fs
+    cam_scale = 10.0
+    if kind == "sphere":
+        sc = load_scene("CBspheres_lambertian")
+        prims = sc.prims[sc.prims["type"] == 1][:1].copy()
+        lights = np.zeros(1, fs.LIGHT_DT)
+    else:
+        sc = load_scene("CBspheres")
+        prims = sc.prims
+        lights = np.concatenate([sc.lights, np.zeros(1, fs.LIGHT_DT)])
+    lights[-1]["type"] = fs.LIGHT_ENV
+    lights[-1]["radiance"] = radiance
+    cam = sc.camera.copy()
+    cam["screen_dist"] = cam["screen_dist"] / cam_scale
+    return fs.FlatScene(cam, sc.materials, lights, prims)

@@ -136,14 +136,35 @@ def sample_replay(name):
     print(name, "sample_f replay:", M, "calls;", int(np.isnan(out[:, 3]).sum()), "left unset by the reference (refraction TIR)")
 
 
+def envmap_units():
+    """EnvironmentLight::sample_dir of the reference on a small synthetic lat-long map (envdir command)."""
+    import subprocess, tempfile
+    rng = np.random.default_rng(77)
+    w, h = 16, 8
+    m = rng.uniform(0.1, 3.0, (h, w, 3)).astype(np.float32).astype(np.float64)
+    d = unit(rng.normal(size=(2000, 3)))
+    d[:6] = [[0, 1, 0], [0, -1, 0], [1, 0, 0], [-1, 0, 0], [0, 0, 1], [0, 0, -1]]     # poles and the seam
+    d = d.astype(np.float32).astype(np.float64)
+    with tempfile.TemporaryDirectory() as td:
+        m.tofile(os.path.join(td, "m.bin")); d.tofile(os.path.join(td, "d.bin"))
+        subprocess.run([O.REF_HARNESS, "envdir", str(w), str(h), "m.bin", "d.bin", "o.bin"], check=True, cwd=td, capture_output=True)
+        out = np.fromfile(os.path.join(td, "o.bin"), np.float64).reshape(-1, 3)
+    np.savez_compressed(os.path.join(OUT, "envmap.units.npz"), map=m.astype(np.float32), dirs=d, out=out)
+    print("envmap units:", out.shape, out.mean())
+
+
 def main():
     only = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if only == "envmap":
+        envmap_units()
+        return
     assert O.have_ref(), "build the reference first: make -C oracle ref"
     os.makedirs(os.path.join(OUT, "scenes"), exist_ok=True)
     for name in EXTRA_SCENES:
         extra_units(name)
     for name in SAMPLE_SCENES:
         sample_replay(name)
+    envmap_units()
     if only == "extra":
         return
     for name, (W, H, ns, m) in SCENES.items():

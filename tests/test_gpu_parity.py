@@ -376,6 +376,90 @@ def test_ragged_frames_and_short_paths_match_oracle(api, O, name, W, H, ns, m):
     assert relmse(ge, oe) <= 2e-3 and relmse(gl, ol) <= 2e-3 and relmse(gs, os_) <= 2e-3
 
 
+# ---------------------------------------------------------------- environment light (extension: no reference behaviour)
+def make_env_renderer(api, kind, w, h, envmap=None, **kw):
+    from conftest import env_scene
+    R = api.Renderer(0, **kw)
+    sc = env_scene(kind)
+    R.set_scene(sc)
+    R.set_frame_size(w, h)
+    if envmap is not None:
+        R.set_environment_map(envmap)
+    return R, sc
+
+
+def test_environment_map_lookup_matches_the_reference(api):
+    """light_eval on the environment light at points of its sphere: Le = map(direction), against the reference's own
+    EnvironmentLight::sample_dir on the same synthetic map (tests/golden/envmap.units.npz)."""
+    g = np.load(os.path.join(GOLDEN, "envmap.units.npz"))
+    R, sc = make_env_renderer(api, "cornell", 64, 48, envmap=g["map"])
+    d = sc.prims["data"]; tri = sc.prims["type"] == 0
+    lo = np.minimum(d[tri, :9].reshape(-1, 3).min(0), (d[~tri, :3] - d[~tri, 3:4]).min(0))
+    hi = np.maximum(d[tri, :9].reshape(-1, 3).max(0), (d[~tri, :3] + d[~tri, 3:4]).max(0))
+    c, rs = (lo + hi) / 2, np.linalg.norm(hi - lo) / 2
+    n = len(g["dirs"])
+    q = np.zeros((n, 7)); q[:, 0] = len(sc.lights) - 1
+    q[:, 1:4] = c + 1000 * rs * g["dirs"]; q[:, 4:7] = g["dirs"]       # wi: toward the light
+    out = R.light_eval(q)
+    assert np.all(out[:, 0] == 1)
+    # (the direction is recovered from an fp32 point 1000 scene radii away: 1e-4 of a texel)
+    assert np.mean(np.abs(out[:, 1:4] - g["out"]) <= 2e-3 * g["out"] + 1e-4) > 0.995
+    assert np.allclose(out[:, 4], 1 / (4 * np.pi * (1000 * rs) ** 2), rtol=1e-5)
+
+
+def test_environment_furnace_known_answers(api):
+    """A convex diffuse sphere (rho = 0.8) under a constant environment L = 1 reflects exactly rho L; the background is
+    L.  Strategy (t=3, s=0) — the eye subpath leaves the scene and meets the environment — gives that without noise;
+    (t=2, s=1) connects a fresh point of the environment, rho L on average."""
+    from test_oracle_vs_golden import sphere_mask
+    from oracle import oracle as O
+    from conftest import env_scene
+    W, H = 48, 36
+    inner, outer = sphere_mask(O.Oracle(env_scene("sphere"), W, H), W, H)
+    R, _ = make_env_renderer(api, "sphere", W, H, ns_aa=8, max_ray_depth=3, seed=1, no_mis=True)
+    R.render(strategy=(3, 0))
+    a = R.framebuffer(0)
+    assert np.allclose(a[inner], 0.8, rtol=1e-5)
+    R.clear(); R.render(strategy=(2, 0))
+    b = R.framebuffer(0)
+    assert np.allclose(b[outer], 1.0, rtol=1e-5) and np.all(b[inner] == 0)
+    R2, _ = make_env_renderer(api, "sphere", W, H, ns_aa=4096, max_ray_depth=3, seed=2, no_mis=True)
+    R2.render(strategy=(2, 1))
+    assert abs(R2.framebuffer(0)[inner].mean() - 0.8) < 0.005
+
+
+@pytest.mark.parametrize("kind,m,envmap", [("sphere", 3, False), ("cornell", 5, False), ("cornell", 5, True), ("sphere", 2, True)])
+def test_environment_render_matches_oracle(api, O, kind, m, envmap):
+    """Environment alone and environment + area light (CBspheres: mirror and glass), constant and with a lat-long map:
+    the CUDA path against the oracle with the same random numbers, image and single samples."""
+    from conftest import env_scene
+    W, H, ns = 48, 36, 8
+    emap = np.load(os.path.join(GOLDEN, "envmap.units.npz"))["map"] if envmap else None
+    R, sc = make_env_renderer(api, kind, W, H, envmap=emap, ns_aa=ns, max_ray_depth=m, seed=13)
+    R.render()
+    gs, ge, gl = (R.framebuffer(i).astype(np.float64) for i in range(3))
+    orc = O.Oracle(sc, W, H)
+    if envmap:
+        orc.set_envmap(emap)
+    os_, oe, ol, _ = orc.render(ns, m, rng_mode=1, seed=13, threads=8)
+    assert np.isfinite(gs).all()
+    assert abs(gs.mean() - os_.mean()) <= 1e-3 * os_.mean()
+    assert relmse(ge, oe) <= 1e-3 and relmse(gl, ol) <= 1e-3 and relmse(gs, os_) <= 1e-3
+    rng = np.random.default_rng(3)
+    n_strat = n_bad = 0
+    for _ in range(30):
+        x, y, k = int(rng.integers(W)), int(rng.integers(H)), int(rng.integers(ns))
+        tg, to = R.trace_sample(x, y, k), orc.trace_sample(ns, m, x, y, k, seed=13)
+        so = {(int(r[0]), int(r[1])): r for r in to["strategies"]}
+        for r in tg["strategies"]:
+            q = so[(int(r[0]), int(r[1]))]
+            g_ill = np.zeros(3) if np.isnan(r[2]) else r[2:5] * r[5]
+            o_ill = np.zeros(3) if np.isnan(q[2]) else q[2:5] * q[5]
+            n_strat += 1
+            n_bad += np.abs(g_ill - o_ill).max() > 2e-3 * (np.abs(o_ill).max() + 1e-2)
+    assert n_strat > 100 and n_bad <= 0.04 * n_strat, (n_bad, n_strat)
+
+
 def test_cell_render_matches_oracle(api, O):
     """bdpt_set_cell (the reference's `-p x y dx dy`): only the cell's pixels are sampled — eye image zero outside it and
     equal to the full render's inside; the light image is what THOSE samples' light subpaths splat, anywhere."""
