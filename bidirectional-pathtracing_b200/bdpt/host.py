@@ -20,6 +20,8 @@ def load_library():
         L.bdpt_host_load_dae.restype = C.c_int
         L.bdpt_host_apply_camera_settings.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
         L.bdpt_host_apply_camera_settings.restype = C.c_int
+        L.bdpt_host_load_envmap.argtypes = [C.c_char_p, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.bdpt_host_load_envmap.restype = C.c_int
         L.bdpt_host_free.argtypes = [C.c_void_p]
         L.bdpt_host_free.restype = None
         L.bdpt_host_last_error.restype = C.c_char_p
@@ -49,3 +51,17 @@ def apply_camera_settings(scene: fs.FlatScene, path: str, width: int, height: in
     if rc != 0:
         raise RuntimeError(f"bdpt_host_apply_camera_settings({path}) failed ({rc}): {L.bdpt_host_last_error().decode()}")
     return fs.FlatScene(cam, scene.materials, scene.lights, scene.prims)
+
+
+def load_envmap(spec: str):
+    """The reference's `-e <path>`: (h, w, 3) float32 lat-long map, row 0 = up (.exr, .pfm or "r,g,b")."""
+    import numpy as np
+    L = load_library()
+    p, w, h = C.POINTER(C.c_float)(), C.c_int(), C.c_int()
+    rc = L.bdpt_host_load_envmap(os.fsencode(spec), C.byref(p), C.byref(w), C.byref(h))
+    if rc != 0:
+        raise RuntimeError(f"bdpt_host_load_envmap({spec}) failed ({rc}): {L.bdpt_host_last_error().decode()}")
+    try:
+        return np.ctypeslib.as_array(p, shape=(h.value, w.value, 3)).copy()
+    finally:
+        L.bdpt_host_free(p)

@@ -168,7 +168,7 @@ __device__ inline bool walk_shade(const Job& J, WalkState& W, Trav& T) {
   const DScene& sc = J.sc;
   const f3 o = T.o, d = T.d;
   if (T.hit.leaf < 0) {
-    if (sc.env_light < 0) return false;
+    if (sc.env_light < 0 || W.kind != 0) return false;   // (a LIGHT subpath's vertex on an emitter carries nothing: f = 0)
     // The ray leaves the scene: it meets the environment's sphere (shading.cuh, "environment light"), whose surface
     // is an emitter — the vertex is stored like any other emissive end of a subpath, and the walk ends there.
     const Light L = load_light(sc, sc.env_light);

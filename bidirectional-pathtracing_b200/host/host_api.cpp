@@ -7,6 +7,7 @@
 #include <string>
 
 #include "dae_scene.h"
+#include "envmap_read.h"
 
 namespace { thread_local std::string g_err; }
 
@@ -28,6 +29,17 @@ int bdpt_host_load_dae(const char* path, int width, int height, unsigned char** 
 int bdpt_host_apply_camera_settings(void* camera, const char* path, int width, int height) {
   if (!camera || !path) return -2;
   return bdpt_host::apply_camera_settings((BdptCamera*)camera, path, width, height, &g_err) ? 0 : -3;
+}
+
+int bdpt_host_load_envmap(const char* spec, float** rgb, int* width, int* height) {
+  if (!spec || !rgb || !width || !height) return -2;
+  bdpt_host::EnvMap m;
+  if (!bdpt_host::read_envmap(spec, &m, &g_err)) return -3;
+  *rgb = (float*)malloc(m.rgb.size() * sizeof(float));
+  if (!*rgb) { g_err = "out of memory"; return -2; }
+  memcpy(*rgb, m.rgb.data(), m.rgb.size() * sizeof(float));
+  *width = m.w; *height = m.h;
+  return 0;
 }
 
 void bdpt_host_free(void* p) { free(p); }

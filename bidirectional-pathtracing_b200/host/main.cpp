@@ -6,8 +6,10 @@
 // worker threads); -l -a -b -d -H are accepted and ignored exactly as the reference's BDPT ignores them;
 // -c <file> loads a camera settings file (Camera::load_settings, camera.cpp:169-186; applied after -r like
 // main.cpp:174-178); -p x y dx dy renders a cell and writes a dx x dy image (render_to_file's cell path,
-// raytraced_renderer.cpp:338-346); -e (environment map) is rejected: the reference's BDPT aborts on environment
-// lights (environment_light.cpp:182-208).
+// raytraced_renderer.cpp:338-346); -e <file> adds an environment light with a lat-long map (.exr / .pfm, or "r,g,b"
+// for a constant one) to the scene's lights like main.cpp:115-118 + raytraced_renderer.cpp:117-119 do — the
+// reference's BDPT then aborts (environment_light.cpp:182-208); what this build renders instead is defined in
+// include/bdpt_flatscene.h (BDPT_LIGHT_ENV).
 // Extra options of this build: -g N (use N GPUs of this box: samples sharded, scene ingested per GPU in parallel
 // host threads, ONE ncclReduce of the accumulators to GPU 0), -S seed, -R (enable the roulette rule the reference ships
 // commented out), -B (balance heuristic), -o scene.fscene (dump the flat scene and exit).
@@ -25,6 +27,7 @@
 
 #include "../../include/bdpt_b200.h"
 #include "dae_scene.h"
+#include "envmap_read.h"
 #include "png_write.h"
 
 static void usage(const char* bin) {
@@ -34,6 +37,7 @@ static void usage(const char* bin) {
   printf("  -l  <INT>        Number of samples per area light (ignored by BDPT)\n");
   printf("  -t  <INT>        Number of render threads (accepted, unused on the GPU)\n");
   printf("  -m  <INT>        Maximum ray depth\n");
+  printf("  -e  <PATH>       Path to environment map (.exr, .pfm, or r,g,b for a constant environment)\n");
   printf("  -f  <FILENAME>   Image (.png) file to save output to\n");
   printf("  -r  <INT> <INT>  Width and height of output image\n");
   printf("  -p  <x> <y> <dx> <dy>  Used with -f and -r to render a cell\n");
@@ -51,7 +55,7 @@ static void usage(const char* bin) {
 int main(int argc, char** argv) {
   int ns = 1, m = 1, threads = 1, W = 0, H = 0, gpus = 1, roulette = 0, balance = 0;
   unsigned long long seed = 0;
-  std::string out_png, out_fscene, cam_settings;
+  std::string out_png, out_fscene, cam_settings, env_spec;
   int cell_x = -1, cell_y = 0, cell_dx = 0, cell_dy = 0;
   int opt;
   while ((opt = getopt(argc, argv, "s:l:t:m:e:hH:f:r:c:b:d:a:p:g:S:RBo:")) != -1) {
@@ -75,7 +79,7 @@ int main(int argc, char** argv) {
       case 'l': case 'b': case 'd': break;                  // no effect on the BDPT image
       case 'a': optind++; break;                              // two arguments, ignored
       case 'H': optind--; break;                              // flag in the reference (main.cpp:131-134)
-      case 'e': MSG("environment maps are not supported by the BDPT integrator (the reference aborts on them)"); return 1;
+      case 'e': env_spec = optarg; break;
       default: usage(argv[0]); return 1;
     }
   }
@@ -88,6 +92,14 @@ int main(int argc, char** argv) {
   std::string err;
   if (!bdpt_host::load_dae(scene_path, &scene, &err)) { MSG("Error: %s", err.c_str()); return 1; }
   if (W <= 0 || H <= 0) { W = 800; H = 600; }
+  bdpt_host::EnvMap envmap;
+  if (!env_spec.empty()) {
+    printf("[PathTracer] Loading environment map %s\n", env_spec.c_str());
+    if (!bdpt_host::read_envmap(env_spec, &envmap, &err)) { MSG("Error: %s", err.c_str()); return 1; }
+    BdptLight e; memset(&e, 0, sizeof e);
+    e.type = BDPT_LIGHT_ENV; e.radiance[0] = e.radiance[1] = e.radiance[2] = 1.0;
+    scene.lights.push_back(e);    // RaytracedRenderer::set_scene appends envLight to the scene's lights (:117-119)
+  }
   if (!cam_settings.empty()) {
     bdpt_host::apply_screen_size(&scene.camera, W, H);    // -r first, then the file (main.cpp:174-178)
     if (!bdpt_host::apply_camera_settings(&scene.camera, cam_settings, W, H, &err)) { MSG("Error: %s", err.c_str()); return 1; }
@@ -121,6 +133,7 @@ int main(int argc, char** argv) {
         int rc = bdpt_upload_scene(ctx[g], &scene.camera, scene.materials.data(), (uint32_t)scene.materials.size(), scene.lights.data(),
                                    (uint32_t)scene.lights.size(), scene.prims.data(), (uint32_t)scene.prims.size());
         if (rc == BDPT_OK) rc = bdpt_set_frame(ctx[g], W, H);
+        if (rc == BDPT_OK && envmap.w > 0) rc = bdpt_set_environment_map(ctx[g], envmap.rgb.data(), envmap.w, envmap.h);
         if (rc == BDPT_OK && cell) rc = bdpt_set_cell(ctx[g], cell_x, cell_y, cell_dx, cell_dy);
         rcs[g] = rc;
       });

@@ -19,6 +19,11 @@ int bdpt_host_load_dae(const char* path, int width, int height, unsigned char** 
  * (bdpt_flatscene.h) in place.  The reference loads the file AFTER `-r` (src/application/main.cpp:174-178): the file's
  * fovs replace the ones Camera::set_screen_size derived; width / height are the frame the camera will render. */
 int bdpt_host_apply_camera_settings(void* camera, const char* path, int width, int height);
+/* The `-e <path>` option (reference src/application/main.cpp:40-78,115-118: OpenEXR through tinyexr): a lat-long
+ * environment map as width x height RGB floats, rows top first (malloc'ed, release with bdpt_host_free), ready for
+ * bdpt_set_environment_map.  spec: an .exr file (single-part scan-line, HALF / FLOAT R G B, compression NONE / RLE /
+ * ZIPS / ZIP), a .pfm file, or "r,g,b" for a constant environment. */
+int bdpt_host_load_envmap(const char* spec, float** rgb, int* width, int* height);
 void bdpt_host_free(void* p);
 const char* bdpt_host_last_error(void);
 #ifdef __cplusplus

@@ -25,6 +25,10 @@
 //       map: W x H x 3 fp64 radiance (row 0 = up); dirs: N x 3; out: N x 3 = EnvironmentLight::sample_dir
 //       (environment_light.cpp:157-165: dir -> theta, phi -> x, y -> bilerp) of a reference EnvironmentLight built
 //       on that map.  (Its constructor writes probability_debug.png into the working directory.)
+//   exr       file.exr out.bin
+//       Decodes the file with the reference's own EXR reader (the vendored tinyexr, called the way load_exr does,
+//       src/application/main.cpp:40-78: half channels requested as float) and writes {width, height, then R G B per
+//       pixel, rows top first} as fp64 — the pin of host/envmap_read.h.
 //   light     scene.dae in.bin out.bin
 //       in: N x {light, p[3], wi[3]} (7 each); out: N x {contain_point, Le[3] (sample_pdf), point_pdf, dir_pdf}
 //   camera    scene.dae W H in.bin out.bin
@@ -55,6 +59,9 @@
 #include <thread>
 #include <unordered_map>
 #include <vector>
+
+#define TINYEXR_IMPLEMENTATION   /* the reference compiles tinyexr into its main.cpp (:4-5); the harness has its own main */
+#include "CGL/tinyexr.h"
 
 // The reference keeps the members we must read (BSDF parameters, camera pose,
 // renderer internals) private; the harness opens them for inspection only.
@@ -294,6 +301,29 @@ int cmd_envdir(int argc, char** argv) {
   return 0;
 }
 
+int cmd_exr(int argc, char** argv) {
+  const char* err = nullptr;
+  EXRImage exr;
+  InitEXRImage(&exr);
+  if (ParseMultiChannelEXRHeaderFromFile(&exr, argv[2], &err) != 0) { fprintf(stderr, "tinyexr: %s\n", err ? err : "?"); return 2; }
+  for (int i = 0; i < exr.num_channels; i++)
+    if (exr.pixel_types[i] == TINYEXR_PIXELTYPE_HALF) exr.requested_pixel_types[i] = TINYEXR_PIXELTYPE_FLOAT;
+  if (LoadMultiChannelEXRFromFile(&exr, argv[2], &err) != 0) { fprintf(stderr, "tinyexr: %s\n", err ? err : "?"); return 2; }
+  int ci[3] = {-1, -1, -1};
+  for (int i = 0; i < exr.num_channels; i++) {
+    if (!strcmp(exr.channel_names[i], "R")) ci[0] = i;
+    if (!strcmp(exr.channel_names[i], "G")) ci[1] = i;
+    if (!strcmp(exr.channel_names[i], "B")) ci[2] = i;
+  }
+  if (ci[0] < 0 || ci[1] < 0 || ci[2] < 0) { fprintf(stderr, "no R G B channels\n"); return 2; }
+  std::vector<double> out;
+  out.push_back(exr.width); out.push_back(exr.height);
+  for (size_t i = 0; i < (size_t)exr.width * exr.height; i++)
+    for (int c = 0; c < 3; c++) out.push_back(((float*)exr.images[ci[c]])[i]);
+  write_doubles(argv[3], out);
+  return 0;
+}
+
 int cmd_light(int argc, char** argv) {
   Loaded L = load_scene(argv[2], 0, 0, 1, 1, 1);
   std::vector<double> in = read_doubles(argv[3]);
@@ -407,6 +437,7 @@ int main(int argc, char** argv) {
   if (c == "bsdf" && argc >= 5) return cmd_bsdf(argc, argv);
   if (c == "bsdf_sample" && argc >= 5) return cmd_bsdf_sample(argc, argv);
   if (c == "envdir" && argc >= 7) return cmd_envdir(argc, argv);
+  if (c == "exr" && argc >= 4) return cmd_exr(argc, argv);
   if (c == "light" && argc >= 5) return cmd_light(argc, argv);
   if (c == "camera" && argc >= 7) return cmd_camera(argc, argv);
   if (c == "render" && argc >= 9) return cmd_render(argc, argv);

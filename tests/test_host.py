@@ -36,7 +36,8 @@ def test_host_library_exports_every_declared_symbol():
     from bdpt import host
     hdr = open(os.path.join(ROOT, "include", "bdpt_host.h")).read()
     declared = sorted(set(re.findall(r"\b(bdpt_host_[a-z0-9_]+)\s*\(", hdr)))
-    assert declared == ["bdpt_host_apply_camera_settings", "bdpt_host_free", "bdpt_host_last_error", "bdpt_host_load_dae"]
+    assert declared == ["bdpt_host_apply_camera_settings", "bdpt_host_free", "bdpt_host_last_error", "bdpt_host_load_dae",
+                        "bdpt_host_load_envmap"]
     lib = host.load_library()
     for name in declared:
         assert hasattr(lib, name)

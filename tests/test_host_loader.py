@@ -280,3 +280,107 @@ def test_cli_camera_file_and_cell(tmp_path):
     assert np.mean(np.abs(img.astype(int) - ref.astype(int)) <= 1) > 0.999
     rate = read_png(str(out)[:-4] + "_rate.png")
     assert rate.shape == (H, W, 4) and (rate[H - y - 1, x, :3] == [255, 0, 0]).all() and (rate[0, 0, :3] == [0, 0, 255]).all()
+
+
+# ------------------------------------------------------------------ `-e <environment map>`: the map readers
+def write_exr(path, img, compression="none", dtype="half", channels=("B", "G", "R")):
+    """Minimal single-part scan-line OpenEXR writer (test input): img (h, w, 3) RGB; compression none / zips / zip."""
+    h, w, _ = img.shape
+    comp = {"none": 0, "rle": 1, "zips": 2, "zip": 3}[compression]
+    ptype, npt = (1, np.float16) if dtype == "half" else (2, np.float32)
+    def attr(name, typ, data):
+        return name.encode() + b"\0" + typ.encode() + b"\0" + struct.pack("<i", len(data)) + data
+    chl = b"".join(c.encode() + b"\0" + struct.pack("<iBBBBii", ptype, 0, 0, 0, 0, 1, 1) for c in sorted(channels)) + b"\0"
+    box = struct.pack("<iiii", 0, 0, w - 1, h - 1)
+    hdr = (struct.pack("<II", 20000630, 2) + attr("channels", "chlist", chl) + attr("compression", "compression", bytes([comp])) +
+           attr("dataWindow", "box2i", box) + attr("displayWindow", "box2i", box) + attr("lineOrder", "lineOrder", b"\0") +
+           attr("pixelAspectRatio", "float", struct.pack("<f", 1.0)) + attr("screenWindowCenter", "v2f", struct.pack("<ff", 0, 0)) +
+           attr("screenWindowWidth", "float", struct.pack("<f", 1.0)) + b"\0")
+    lines = 16 if comp == 3 else 1
+    idx = {"R": 0, "G": 1, "B": 2}
+    blocks = []
+    for y0 in range(0, h, lines):
+        raw = b"".join(img[y, :, idx[c]].astype(npt).tobytes() for y in range(y0, min(h, y0 + lines)) for c in sorted(channels))
+        data = raw
+        if comp in (2, 3):
+            a = np.frombuffer(raw, np.uint8)
+            t = np.concatenate([a[0::2], a[1::2]]).astype(np.int32)            # interleave
+            t[1:] = (t[1:] - t[:-1] + 128 + 256) % 256                          # predictor
+            z = zlib.compress(t.astype(np.uint8).tobytes())
+            data = z if len(z) < len(raw) else raw
+        blocks.append(struct.pack("<ii", y0, len(data)) + data)
+    off = len(hdr) + 8 * len(blocks)
+    table = b""
+    for b in blocks:
+        table += struct.pack("<Q", off); off += len(b)
+    open(path, "wb").write(hdr + table + b"".join(blocks))
+
+
+@pytest.mark.parametrize("compression,dtype", [("none", "float"), ("none", "half"), ("zips", "half"), ("zip", "float"), ("zip", "half")])
+def test_exr_reader_against_the_reference_reader(tmp_path, compression, dtype):
+    """host/envmap_read.h against the reference's OWN EXR reader (the vendored tinyexr, called like load_exr does,
+    main.cpp:40-78 — ref_harness exr) on files an independent writer made: every pixel identical."""
+    from bdpt import host
+    from oracle import oracle as O
+    if not O.have_ref():
+        pytest.skip("needs oracle/_ref/ref_harness")
+    # 37 rows: a ragged last ZIP block.  Smooth and coarsely quantised so that every block really compresses (the
+    # reference's tinyexr has no path for the "stored raw because compression did not help" case of the format)
+    yy, xx = np.mgrid[0:37, 0:50]
+    img = np.stack([np.round(8 * (1 + np.sin(xx / 7.0)) * (1 + yy / 9.0)) / 4, np.round(xx / 5.0) * 0.5 + 0.25, np.round(16 * np.exp(yy / 12.0)) / 16], -1).astype(np.float32)
+    img[0, 0] = [0, 2.0 ** -14, 6e4]
+    f = tmp_path / "env.exr"
+    write_exr(str(f), img, compression, dtype)
+    got = host.load_envmap(str(f))
+    out = tmp_path / "ref.bin"
+    subprocess.run([O.REF_HARNESS, "exr", str(f), str(out)], check=True, capture_output=True)
+    ref = np.fromfile(out, np.float64)
+    assert (ref[0], ref[1]) == (50, 37)
+    ref = ref[2:].reshape(37, 50, 3).astype(np.float32)
+    assert got.shape == (37, 50, 3)
+    assert np.array_equal(got, ref)
+    want = img.astype(np.float16).astype(np.float32) if dtype == "half" else img
+    assert np.array_equal(got, want)
+
+
+def test_pfm_and_constant_environment_maps(tmp_path):
+    from bdpt import host
+    img = np.arange(4 * 6 * 3, dtype=np.float32).reshape(4, 6, 3)
+    f = tmp_path / "e.pfm"
+    open(f, "wb").write(b"PF\n6 4\n-1.0\n" + img[::-1].astype("<f4").tobytes())   # little-endian, bottom row first
+    assert np.array_equal(host.load_envmap(str(f)), img)
+    c = host.load_envmap("0.5,2,3.5")
+    assert c.shape == (2, 1, 3) and np.array_equal(c[0, 0], [0.5, 2, 3.5])
+    with pytest.raises(RuntimeError):
+        host.load_envmap(str(tmp_path / "missing.exr"))
+
+
+@pytest.mark.gpu
+def test_cli_environment_map(tmp_path):
+    """`pathtracer -e map.exr`: the environment light joins the scene's lights (raytraced_renderer.cpp:117-119) and the
+    image equals what the library renders for the same scene and map."""
+    from bdpt import api, host, flatscene as fs
+    dae = find_dae(CASES["CBspheres"])
+    if dae is None:
+        pytest.skip("no .dae input on this box")
+    W, H, ns, m = 96, 72, 16, 4
+    rng = np.random.default_rng(4)
+    env = rng.uniform(0.2, 2.0, (8, 16, 3)).astype(np.float32)
+    f = tmp_path / "env.exr"
+    write_exr(str(f), env, "zip", "float")
+    exe = os.path.join(ROOT, "bidirectional-pathtracing_b200", "host", "pathtracer")
+    out = tmp_path / "e.png"
+    r = subprocess.run([exe, "-s", str(ns), "-m", str(m), "-r", str(W), str(H), "-e", str(f), "-f", str(out), dae], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Loading environment map" in r.stdout
+    img = read_png(str(out))
+    sc = host.load_dae(dae)
+    lights = np.concatenate([sc.lights, np.zeros(1, fs.LIGHT_DT)])
+    lights[-1]["type"] = fs.LIGHT_ENV; lights[-1]["radiance"] = 1.0
+    R = api.Renderer(0, ns_aa=ns, max_ray_depth=m, seed=0)
+    R.set_scene(fs.FlatScene(sc.camera, sc.materials, lights, sc.prims)); R.set_frame_size(W, H)
+    R.set_environment_map(host.load_envmap(str(f))); R.render()
+    ref = R.tonemap(0)
+    assert np.mean(np.abs(img.astype(int) - ref.astype(int)) <= 1) > 0.999
+    P = api.Renderer(0, ns_aa=ns, max_ray_depth=m, seed=0); P.set_scene(sc); P.set_frame_size(W, H); P.render()
+    assert np.mean(np.abs(P.tonemap(0).astype(int) - ref.astype(int)) <= 1) < 0.9      # the environment does light the scene
