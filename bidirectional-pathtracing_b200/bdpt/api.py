@@ -50,7 +50,7 @@ class Stats(C.Structure):
 
 
 EXPORTS = ["bdpt_create", "bdpt_destroy", "bdpt_last_error", "bdpt_set_stream", "bdpt_upload_scene",
-           "bdpt_set_camera", "bdpt_set_environment_map", "bdpt_set_frame", "bdpt_set_cell", "bdpt_clear", "bdpt_render", "bdpt_read_framebuffer",
+           "bdpt_set_camera", "bdpt_set_environment_map", "bdpt_set_frame", "bdpt_set_lens", "bdpt_set_cell", "bdpt_clear", "bdpt_render", "bdpt_read_framebuffer",
            "bdpt_framebuffer_device", "bdpt_tonemap_rgba8", "bdpt_get_stats", "bdpt_intersect_batch",
            "bdpt_occluded_batch", "bdpt_bsdf_eval_batch", "bdpt_bsdf_sample_batch", "bdpt_light_eval_batch",
            "bdpt_camera_eval_batch", "bdpt_trace_sample", "bdpt_host_build_bvh", "bdpt_device_bvh",
@@ -78,6 +78,7 @@ def load_library():
     L.bdpt_set_camera.argtypes = [vp, vp]
     L.bdpt_set_environment_map.argtypes = [vp, vp, C.c_int, C.c_int]
     L.bdpt_set_frame.argtypes = [vp, C.c_int, C.c_int]
+    L.bdpt_set_lens.argtypes = [vp, C.c_double, C.c_double]
     L.bdpt_set_cell.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
     L.bdpt_clear.argtypes = [vp]
     L.bdpt_render.argtypes = [vp, C.POINTER(RenderParams)]
@@ -176,6 +177,10 @@ class Renderer:
     def set_frame_size(self, width: int, height: int):
         self._ck(self.L.bdpt_set_frame(self.h, width, height))
         self.W, self.H = width, height
+
+    def set_lens(self, lens_radius: float, focal_distance: float):
+        """Thin lens (extension; the reference's BDPT is a pinhole whatever -b / -d say); radius 0 = pinhole."""
+        self._ck(self.L.bdpt_set_lens(self.h, lens_radius, focal_distance))
 
     def set_cell(self, x: int = 0, y: int = 0, dx: int = 0, dy: int = 0):
         """The reference's cell render (`-p x y dx dy`); dx = dy = 0: the whole frame again."""

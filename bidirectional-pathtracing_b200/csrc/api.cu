@@ -56,6 +56,7 @@ struct BdptContext {
   float* resolve_tmp = nullptr;
   uint8_t* rgba_tmp = nullptr;
   int ns_last = 1;
+  float lens_radius = 0.f, focal_dist = 4.7f;   // bdpt_set_lens
   int cell[4] = {0, 0, 0, 0};   // x, y, dx, dy of a cell render (bdpt_set_cell); dx = 0: the whole frame
 
   // batch storage
@@ -149,6 +150,7 @@ void make_dcamera(const BdptCamera& c, int W, int H, DCamera* out) {
   out->tan_v = (float)std::tan(vfov * PI / 360);
   out->nclip = (float)c.nclip; out->fclip = (float)c.fclip;
   out->W = W; out->H = H;
+  out->lens_radius = 0.f; out->focal_dist = 1.f;   // (bdpt_set_lens fills these in)
 }
 
 // fp32 bounds of what the kernels actually test: the fp32-narrowed triangle, a slightly padded sphere
@@ -230,6 +232,7 @@ cudaEvent_t get_event(BdptContext* ctx, size_t i) {
 void fill_job(BdptContext* ctx, const BdptRenderParams* p, Job* J) {
   memset(J, 0, sizeof(Job));
   J->sc = ctx->sc; J->cam = ctx->cam; J->point_lights = ctx->point_lights;
+  J->cam.lens_radius = ctx->lens_radius; J->cam.focal_dist = ctx->focal_dist;
   J->v0 = ctx->v0; J->counts = ctx->counts;
   J->q0 = ctx->q0; J->q2 = ctx->q2; J->qctr = ctx->qctr; J->chunks = ctx->chunks;
   J->acc_eye = ctx->acc_eye; J->acc_light = ctx->acc_light; J->stats = ctx->d_stats; J->dbg = nullptr;
@@ -740,6 +743,13 @@ int bdpt_set_frame(BdptContext* ctx, int width, int height) {
   }
   make_dcamera(ctx->cam_base, ctx->W, ctx->H, &ctx->cam);
   return bdpt_clear(ctx);
+}
+
+int bdpt_set_lens(BdptContext* ctx, double lens_radius, double focal_distance) {
+  if (!ctx) return BDPT_ERR_ARG;
+  if (!(lens_radius >= 0.0) || (lens_radius > 0.0 && !(focal_distance > 0.0))) return fail(ctx, BDPT_ERR_ARG, "bad lens parameters");
+  ctx->lens_radius = (float)lens_radius; ctx->focal_dist = (float)(lens_radius > 0.0 ? focal_distance : 1.0);
+  return BDPT_OK;
 }
 
 int bdpt_set_cell(BdptContext* ctx, int x, int y, int dx, int dy) {

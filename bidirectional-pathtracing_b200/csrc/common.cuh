@@ -83,6 +83,9 @@ struct DCamera {
   float tan_h, tan_v;  // tan(hFov/2), tan(vFov/2)   (camera.cpp:200-201)
   float nclip, fclip;
   int W, H;
+  // thin lens (camera.h lensRadius / focalDistance, -b / -d).  The reference's BDPT never reads them:
+  // lens_radius > 0 switches on the extension of shading.cuh ("thin lens")
+  float lens_radius, focal_dist;
 };
 
 struct alignas(16) Node8 {  // 80 bytes, see bvh8.h

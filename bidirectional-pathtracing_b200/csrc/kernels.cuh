@@ -138,6 +138,10 @@ __device__ inline bool walk_begin(const Job& J, unsigned i, WalkState& W, Trav& 
   f3 o, d;
   if (W.kind == 0) {
     float sx = W.rng.uniform(), sy = W.rng.uniform();
+    if (J.cam.lens_radius > 0.f) {   // thin lens (extension): two more draws, the eye subpath starts on the lens
+      const float u1 = W.rng.uniform(), u2 = W.rng.uniform();
+      camera_generate_ray_lens(J.cam, ((float)x + sx) / (float)J.cam.W, ((float)y + sy) / (float)J.cam.H, u1, u2, &o, &d);
+    } else
     camera_generate_ray(J.cam, ((float)x + sx) / (float)J.cam.W, ((float)y + sy) / (float)J.cam.H, &o, &d);
     W.prev_n = d; W.alpha = mk3(1.f); W.prev_pdf = 1.f;
     W.pdfeval_prev = 1.f; W.D_prev = 1.f; W.S_prev = 0.f;
@@ -468,7 +472,14 @@ __global__ void __launch_bounds__(BDPT_CONNECT_NT, MINB) k_connect(const Job J) 
         f3 eye_alpha = E.alpha;
         if (t == 1) {
           f3 wi; float dd;
-          float We = camera_sample_ray_pdf(J.cam, Lv.pos, &wi, &dd, &cam_dir_pdf, &eye_x, &eye_y);
+          float We;
+          if (J.cam.lens_radius > 0.f) {   // thin lens (extension): a fresh point of the lens, stream 64 + s
+            Rng r2;
+            r2.begin(J.seed, (unsigned long long)pix_own, (unsigned long long)s_smp[j], 64u + (uint32_t)s);
+            const float u1 = r2.uniform(), u2 = r2.uniform();
+            We = camera_sample_ray_pdf_lens(J.cam, Lv.pos, lens_point(J.cam, u1, u2), &ve_pos, &wi, &dd, &cam_dir_pdf, &eye_x, &eye_y);
+          } else
+          We = camera_sample_ray_pdf(J.cam, Lv.pos, &wi, &dd, &cam_dir_pdf, &eye_x, &eye_y);
           ve_n = -wi;
           eye_alpha = mk3(We);
           // a connection that leaves the frame never reaches the queue

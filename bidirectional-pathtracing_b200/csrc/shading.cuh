@@ -430,6 +430,49 @@ __device__ inline void camera_generate_ray(const DCamera& c, float x, float y, f
   *d = normalized(w);
 }
 
+// ---- thin lens: an extension.  The reference has Camera::generate_ray_for_thin_lens (camera_lens.cpp:22-43) but its
+// BDPT never calls it.  With lens_radius > 0 the eye subpath starts at a uniformly sampled point of the
+// lens (that function, verbatim) and a light-tracing connection (t = 1) goes through a fresh point of the lens: the
+// formulas of sample_ray_pdf with the lens point in place of the pinhole and the angle of the actual ray; the raster
+// position is that of the sensor sample whose rays converge where this ray meets the plane of focus.  t = 0 (a light
+// subpath that hits the lens) is not a strategy here.
+__device__ inline f3 lens_point(const DCamera& c, float rnd_r, float rnd_u) {   // camera space, z = 0
+  float sn, cs;
+  sincos_2pi(rnd_u, &sn, &cs);
+  const float r = c.lens_radius * sqrtf(rnd_r);
+  return mk3(r * cs, r * sn, 0.f);
+}
+// Camera::generate_ray_for_thin_lens camera_lens.cpp:22-43 (rndTheta = 2 pi rnd_u)
+__device__ inline void camera_generate_ray_lens(const DCamera& c, float x, float y, float rnd_r, float rnd_u, f3* o, f3* d) {
+  const f3 pl = lens_point(c, rnd_r, rnd_u);
+  const f3 pf = mk3((2.f * x - 1.f) * c.tan_h, (2.f * y - 1.f) * c.tan_v, -1.f) * c.focal_dist;
+  const f3 dir = pf - pl;
+  *o = c.pos + pl.x * c.c2w_x + pl.y * c.c2w_y;
+  *d = normalized(dir.x * c.c2w_x + dir.y * c.c2w_y + dir.z * c.c2w_z);
+}
+// returns We; *eye = the lens point (world), wi from p toward it
+__device__ inline float camera_sample_ray_pdf_lens(const DCamera& c, f3 p, f3 lens_c, f3* eye, f3* wi, float* dist, float* dir_pdf, int* px, int* py) {
+  *eye = c.pos + lens_c.x * c.c2w_x + lens_c.y * c.c2w_y;
+  const f3 v = *eye - p;
+  *dist = norm(v);
+  *wi = v * (1.0f / *dist);
+  const f3 mw = -(*wi);
+  const f3 wc = mk3(dot(c.w2c_r0, mw), dot(c.w2c_r1, mw), dot(c.w2c_r2, mw));   // lens -> p, camera space
+  const float cos_t = -wc.z;
+  const float c2 = cos_t * cos_t;
+  const float We = c2 * c2 / (4.f * c.tan_h * c.tan_v);
+  *dir_pdf = (*dist * *dist) / cos_t;
+  *px = -1; *py = -1;
+  if (cos_t > 0.f) {
+    const float sf = c.focal_dist / cos_t;
+    const float qx = (lens_c.x + wc.x * sf) / c.focal_dist, qy = (lens_c.y + wc.y * sf) / c.focal_dist;
+    const float fx = ((qx / c.tan_h + 1.f) * 0.5f) * (float)c.W, fy = ((qy / c.tan_v + 1.f) * 0.5f) * (float)c.H;
+    *px = (fx > -2.0e9f && fx < 2.0e9f) ? __float2int_rz(fx) : -1;
+    *py = (fy > -2.0e9f && fy < 2.0e9f) ? __float2int_rz(fy) : -1;
+  }
+  return We;
+}
+
 // Camera::sample_ray_pdf camera.cpp:214-248.  Returns We (a scalar; the reference returns it in all
 // three channels); wi points from p to the pinhole.
 __device__ inline float camera_sample_ray_pdf(const DCamera& c, f3 p, f3* wi, float* dist, float* dir_pdf, int* px, int* py) {

@@ -45,6 +45,8 @@ static void usage(const char* bin) {
   printf("  -g  <INT>        Number of GPUs to shard the samples over (default 1)\n");
   printf("  -S  <INT>        Random seed (default 0)\n");
   printf("  -R               Russian roulette (off in the reference)\n");
+  printf("  -b  <FLOAT>      The size of the aperture  / -d <FLOAT> the focal distance: like the reference's BDPT, ignored unless\n");
+  printf("  -L               ... thin-lens camera for BDPT (extension)\n");
   printf("  -B               Balance heuristic for MIS (the reference uses the power heuristic, beta = 2)\n");
   printf("  -o  <FILENAME>   Write the flat scene (.fscene) and exit\n");
   printf("  -h               Print this help message\n\n");
@@ -57,8 +59,10 @@ int main(int argc, char** argv) {
   unsigned long long seed = 0;
   std::string out_png, out_fscene, cam_settings, env_spec;
   int cell_x = -1, cell_y = 0, cell_dx = 0, cell_dy = 0;
+  double lens_radius = 0.0, focal_distance = 4.7;   // -b / -d (application.h:43-87 defaults: 0 / 4.7)
+  int use_lens = 0;
   int opt;
-  while ((opt = getopt(argc, argv, "s:l:t:m:e:hH:f:r:c:b:d:a:p:g:S:RBo:")) != -1) {
+  while ((opt = getopt(argc, argv, "s:l:t:m:e:hH:f:r:c:b:d:a:p:g:S:RBLo:")) != -1) {
     switch (opt) {
       case 'f': out_png = optarg; break;
       case 'r': W = atoi(argv[optind - 1]); H = optind < argc ? atoi(argv[optind]) : 0; optind++; break;
@@ -76,7 +80,10 @@ int main(int argc, char** argv) {
         cell_x = atoi(argv[optind - 1]); cell_y = atoi(argv[optind]); cell_dx = atoi(argv[optind + 1]); cell_dy = atoi(argv[optind + 2]);
         optind += 3;
         break;
-      case 'l': case 'b': case 'd': break;                  // no effect on the BDPT image
+      case 'b': lens_radius = atof(optarg); break;          // kept, but like the reference's BDPT only honoured ...
+      case 'd': focal_distance = atof(optarg); break;
+      case 'L': use_lens = 1; break;                         // ... when -L asks for the thin-lens extension
+      case 'l': break;                                       // no effect on the BDPT image
       case 'a': optind++; break;                              // two arguments, ignored
       case 'H': optind--; break;                              // flag in the reference (main.cpp:131-134)
       case 'e': env_spec = optarg; break;
@@ -133,6 +140,7 @@ int main(int argc, char** argv) {
         int rc = bdpt_upload_scene(ctx[g], &scene.camera, scene.materials.data(), (uint32_t)scene.materials.size(), scene.lights.data(),
                                    (uint32_t)scene.lights.size(), scene.prims.data(), (uint32_t)scene.prims.size());
         if (rc == BDPT_OK) rc = bdpt_set_frame(ctx[g], W, H);
+        if (rc == BDPT_OK && use_lens) rc = bdpt_set_lens(ctx[g], lens_radius, focal_distance);
         if (rc == BDPT_OK && envmap.w > 0) rc = bdpt_set_environment_map(ctx[g], envmap.rgb.data(), envmap.w, envmap.h);
         if (rc == BDPT_OK && cell) rc = bdpt_set_cell(ctx[g], cell_x, cell_y, cell_dx, cell_dy);
         rcs[g] = rc;

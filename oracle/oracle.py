@@ -41,6 +41,8 @@ def lib():
         L.oracle_set_frame.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.oracle_set_cell.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.oracle_set_envmap.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.oracle_set_lens.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.oracle_lens_ray.argtypes = [C.c_void_p, dp, C.c_long, dp]
         for name in ("oracle_intersect", "oracle_intersect_brute", "oracle_bsdf_eval", "oracle_bsdf_sample",
                      "oracle_light_eval", "oracle_camera_eval"):
             getattr(L, name).argtypes = [C.c_void_p, dp, C.c_long, dp]
@@ -84,6 +86,13 @@ class Oracle:
     def set_frame(self, w: int, h: int) -> None:
         lib().oracle_set_frame(self.h, w, h)
         self.W, self.H = w, h
+
+    def set_lens(self, radius: float, focal_distance: float) -> None:
+        """Thin lens (-b radius, -d focal distance); radius 0 = the pinhole the reference's BDPT always uses."""
+        lib().oracle_set_lens(self.h, radius, focal_distance)
+
+    def lens_ray(self, q):
+        return self._batch("oracle_lens_ray", q, 4, 6)
 
     def set_envmap(self, rgb) -> None:
         """Lat-long radiance map (h, w, 3) float32 of the environment light, row 0 = up; None removes it."""

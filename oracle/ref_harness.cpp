@@ -29,6 +29,9 @@
 //       Decodes the file with the reference's own EXR reader (the vendored tinyexr, called the way load_exr does,
 //       src/application/main.cpp:40-78: half channels requested as float) and writes {width, height, then R G B per
 //       pixel, rows top first} as fp64 — the pin of host/envmap_read.h.
+//   lensray   scene.dae W H lensRadius focalDistance in.bin out.bin
+//       in: N x {x, y, rndR, rndTheta}; out: N x {o[3], d[3]} = Camera::generate_ray_for_thin_lens
+//       (camera_lens.cpp:22-43) of the scene's placed camera.
 //   light     scene.dae in.bin out.bin
 //       in: N x {light, p[3], wi[3]} (7 each); out: N x {contain_point, Le[3] (sample_pdf), point_pdf, dir_pdf}
 //   camera    scene.dae W H in.bin out.bin
@@ -324,6 +327,22 @@ int cmd_exr(int argc, char** argv) {
   return 0;
 }
 
+int cmd_lensray(int argc, char** argv) {
+  size_t W = atoi(argv[3]), H = atoi(argv[4]);
+  Loaded L = load_scene(argv[2], W, H, 1, 1, 1);
+  Camera* c = L.rr->camera;
+  c->lensRadius = atof(argv[5]); c->focalDistance = atof(argv[6]);
+  std::vector<double> in = read_doubles(argv[7]);
+  size_t n = in.size() / 4;
+  std::vector<double> out(n * 6);
+  for (size_t i = 0; i < n; i++) {
+    Ray r = c->generate_ray_for_thin_lens(in[4 * i], in[4 * i + 1], in[4 * i + 2], in[4 * i + 3]);
+    put3(&out[6 * i], r.o); put3(&out[6 * i + 3], r.d);
+  }
+  write_doubles(argv[8], out);
+  return 0;
+}
+
 int cmd_light(int argc, char** argv) {
   Loaded L = load_scene(argv[2], 0, 0, 1, 1, 1);
   std::vector<double> in = read_doubles(argv[3]);
@@ -438,6 +457,7 @@ int main(int argc, char** argv) {
   if (c == "bsdf_sample" && argc >= 5) return cmd_bsdf_sample(argc, argv);
   if (c == "envdir" && argc >= 7) return cmd_envdir(argc, argv);
   if (c == "exr" && argc >= 4) return cmd_exr(argc, argv);
+  if (c == "lensray" && argc >= 9) return cmd_lensray(argc, argv);
   if (c == "light" && argc >= 5) return cmd_light(argc, argv);
   if (c == "camera" && argc >= 7) return cmd_camera(argc, argv);
   if (c == "render" && argc >= 9) return cmd_render(argc, argv);

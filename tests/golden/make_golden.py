@@ -153,10 +153,23 @@ def envmap_units():
     print("envmap units:", out.shape, out.mean())
 
 
+def lens_units():
+    """Camera::generate_ray_for_thin_lens (camera_lens.cpp:22-43) of the reference, CBspheres camera at 480x360."""
+    rng = np.random.default_rng(78)
+    q = rng.uniform(0, 1, (1500, 4)); q[:, 3] *= 2 * np.pi
+    q = q.astype(np.float32).astype(np.float64)
+    out = O.ref_batch("lensray", O.ref_scene("CBspheres"), q, 4, 6, extra=(480, 360, 0.125, 4.5))
+    np.savez_compressed(os.path.join(OUT, "lens.units.npz"), q=q, out=out, params=np.array([480, 360, 0.125, 4.5]))
+    print("lens units:", out.shape)
+
+
 def main():
     only = sys.argv[1] if len(sys.argv) > 1 else "all"
     if only == "envmap":
         envmap_units()
+        return
+    if only == "lens":
+        lens_units()
         return
     assert O.have_ref(), "build the reference first: make -C oracle ref"
     os.makedirs(os.path.join(OUT, "scenes"), exist_ok=True)
@@ -165,6 +178,7 @@ def main():
     for name in SAMPLE_SCENES:
         sample_replay(name)
     envmap_units()
+    lens_units()
     if only == "extra":
         return
     for name, (W, H, ns, m) in SCENES.items():

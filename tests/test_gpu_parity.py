@@ -460,6 +460,55 @@ def test_environment_render_matches_oracle(api, O, kind, m, envmap):
     assert n_strat > 100 and n_bad <= 0.04 * n_strat, (n_bad, n_strat)
 
 
+# ---------------------------------------------------------------------------- thin lens (extension)
+@pytest.mark.parametrize("name,radius,focus", [("CBspheres", 0.1, 4.5), ("CBspheres_lambertian", 0.3, 3.0), ("CBempty", 0.2, 4.0)])
+def test_thin_lens_render_matches_oracle(api, O, name, radius, focus):
+    """bdpt_set_lens: eye subpaths from Camera::generate_ray_for_thin_lens, t = 1 connections through a sampled lens
+    point — the CUDA path against the oracle with the same random numbers (image and single samples)."""
+    W, H, ns, m = 64, 48, 8, 4
+    R = make_renderer(api, name, W, H, ns_aa=ns, max_ray_depth=m, seed=17)
+    R.set_lens(radius, focus)
+    R.render()
+    gs, ge, gl = (R.framebuffer(i).astype(np.float64) for i in range(3))
+    orc = O.Oracle(load_scene(name), W, H)
+    orc.set_lens(radius, focus)
+    os_, oe, ol, _ = orc.render(ns, m, rng_mode=1, seed=17, threads=8)
+    assert np.isfinite(gs).all() and abs(gs.mean() - os_.mean()) <= 1e-3 * os_.mean()
+    assert relmse(ge, oe) <= 1e-3 and relmse(gl, ol) <= 1e-3 and relmse(gs, os_) <= 1e-3
+    rng = np.random.default_rng(3)
+    n_strat = n_bad = 0
+    for _ in range(30):
+        x, y, k = int(rng.integers(W)), int(rng.integers(H)), int(rng.integers(ns))
+        tg, to = R.trace_sample(x, y, k), orc.trace_sample(ns, m, x, y, k, seed=17)
+        so = {(int(r[0]), int(r[1])): r for r in to["strategies"]}
+        for r in tg["strategies"]:
+            q = so.get((int(r[0]), int(r[1])))
+            if q is None:
+                continue
+            g_ill = np.zeros(3) if np.isnan(r[2]) else r[2:5] * r[5]
+            o_ill = np.zeros(3) if np.isnan(q[2]) else q[2:5] * q[5]
+            n_strat += 1
+            n_bad += np.abs(g_ill - o_ill).max() > 2e-3 * (np.abs(o_ill).max() + 1e-2)
+    assert n_strat > 200 and n_bad <= 0.04 * n_strat, (n_bad, n_strat)
+
+
+def test_thin_lens_known_answers(api):
+    """A vanishing lens renders the pinhole's image (same expectation, other random numbers); a wide lens focused in front
+    of the box softens the eye image and keeps its energy; radius 0 IS the pinhole path, bit for bit."""
+    name, W, H, ns, m = "CBspheres", 96, 72, 64, 4
+    P = make_renderer(api, name, W, H, ns_aa=ns, max_ray_depth=m, seed=2); P.render()
+    pin = [P.framebuffer(i) for i in range(3)]
+    Z = make_renderer(api, name, W, H, ns_aa=ns, max_ray_depth=m, seed=2); Z.set_lens(0.0, 4.5); Z.render()
+    assert np.allclose(Z.framebuffer(0), pin[0], rtol=2e-5, atol=1e-6)
+    T = make_renderer(api, name, W, H, ns_aa=ns, max_ray_depth=m, seed=2); T.set_lens(1e-7, 4.5); T.render()
+    assert relmse(T.framebuffer(0), pin[0]) < 0.05 and abs(T.framebuffer(0).mean() - pin[0].mean()) < 0.01 * pin[0].mean()
+    Wd = make_renderer(api, name, W, H, ns_aa=ns, max_ray_depth=m, seed=2); Wd.set_lens(0.5, 1.5); Wd.render()
+    grad = lambda im: np.abs(np.diff(im.mean(-1), axis=1)).mean()
+    assert grad(Wd.framebuffer(1)) < 0.9 * grad(pin[1])
+    with pytest.raises(api.BdptError, match="lens"):
+        Wd.set_lens(0.1, 0.0)
+
+
 def test_cell_render_matches_oracle(api, O):
     """bdpt_set_cell (the reference's `-p x y dx dy`): only the cell's pixels are sampled — eye image zero outside it and
     equal to the full render's inside; the light image is what THOSE samples' light subpaths splat, anywhere."""

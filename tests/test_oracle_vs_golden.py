@@ -145,6 +145,35 @@ def test_environment_map_scales_the_radiance():
     assert img[outer].min() >= 0.1 * 0.5 - 1e-9 and img[outer].max() <= 3.0 * 2.0 + 1e-9 and img[outer].std() > 0.05
 
 
+# ------------------------------------------------------------------ thin lens (extension)
+def test_thin_lens_rays_match_the_reference():
+    """Camera::generate_ray_for_thin_lens (camera_lens.cpp:22-43) of the reference — which its BDPT never calls
+     — on the placed CBspheres camera: bit-identical origins and directions."""
+    g = np.load(os.path.join(GOLDEN, "lens.units.npz"))
+    W, H, a, f = g["params"]
+    orc = O.Oracle(load_scene("CBspheres"), int(W), int(H))
+    orc.set_lens(float(a), float(f))
+    assert np.array_equal(orc.lens_ray(g["q"]), g["out"])
+
+
+def test_thin_lens_known_answers():
+    """The extension's known answers: a vanishing lens is the pinhole; a finite lens blurs what is out of focus and
+    leaves the frame's total energy where it was (eye image: the (t >= 2) strategies)."""
+    from conftest import env_scene
+    W, H, ns, m = 48, 36, 64, 3
+    sc = env_scene("cornell")
+    pin = O.Oracle(sc, W, H).render(ns, m, rng_mode=1, seed=5, threads=8)
+    tiny = O.Oracle(sc, W, H); tiny.set_lens(1e-9, 4.5)
+    a = tiny.render(ns, m, rng_mode=1, seed=5, threads=8)
+    # (the lens draws two more uniforms per eye subpath: other random numbers, the same expectation)
+    assert abs(a[0].mean() - pin[0].mean()) < 0.02 * pin[0].mean()
+    wide = O.Oracle(sc, W, H); wide.set_lens(0.5, 1.5)        # focused far in front of the box
+    b = wide.render(ns, m, rng_mode=1, seed=5, threads=8)
+    grad = lambda im: np.abs(np.diff(im.mean(-1), axis=1)).mean()
+    assert grad(b[1]) < 0.9 * grad(pin[1])                      # defocus: softer eye image
+    assert abs(b[1].mean() - pin[1].mean()) < 0.1 * pin[1].mean()
+
+
 def test_reference_streams_render(scene_case):
     """rng_mode 0 reproduces the reference's `-t 1` render bit for bit (sum, eye, light, ray count)."""
     name, sc, orc = scene_case
