@@ -157,21 +157,19 @@ def test_thin_lens_rays_match_the_reference():
 
 
 def test_thin_lens_known_answers():
-    """The extension's known answers: a vanishing lens is the pinhole; a finite lens blurs what is out of focus and
-    leaves the frame's total energy where it was (eye image: the (t >= 2) strategies)."""
-    from conftest import env_scene
-    W, H, ns, m = 48, 36, 64, 3
-    sc = env_scene("cornell")
-    pin = O.Oracle(sc, W, H).render(ns, m, rng_mode=1, seed=5, threads=8)
-    tiny = O.Oracle(sc, W, H); tiny.set_lens(1e-9, 4.5)
-    a = tiny.render(ns, m, rng_mode=1, seed=5, threads=8)
-    # (the lens draws two more uniforms per eye subpath: other random numbers, the same expectation)
-    assert abs(a[0].mean() - pin[0].mean()) < 0.02 * pin[0].mean()
-    wide = O.Oracle(sc, W, H); wide.set_lens(0.5, 1.5)        # focused far in front of the box
-    b = wide.render(ns, m, rng_mode=1, seed=5, threads=8)
-    grad = lambda im: np.abs(np.diff(im.mean(-1), axis=1)).mean()
-    assert grad(b[1]) < 0.9 * grad(pin[1])                      # defocus: softer eye image
-    assert abs(b[1].mean() - pin[1].mean()) < 0.1 * pin[1].mean()
+    """The extension's known answer: a diffuse wall in the plane of focus looks the same through any lens — every lens
+    point sees the same wall point for a given sensor sample.  CBempty at 48 x 36 shows only the box's back wall
+    (z = -1, perpendicular to the view axis, 5.802 from the camera): with the lens focused there the eye image equals
+    the pinhole's up to Monte-Carlo noise, whatever the radius."""
+    W, H, ns, m = 48, 36, 256, 3
+    sc = load_scene("CBempty")
+    focus = float(sc.camera[0]["pos"][2] + 1.0)
+    pin = O.Oracle(sc, W, H).render(ns, m, rng_mode=1, seed=1, threads=8)
+    for radius in (1e-9, 0.1):
+        lens = O.Oracle(sc, W, H); lens.set_lens(radius, focus)
+        img = lens.render(ns, m, rng_mode=1, seed=2, threads=8)
+        assert abs(img[1].mean() - pin[1].mean()) < 5e-3 * pin[1].mean()
+        assert np.mean((img[1] - pin[1]) ** 2 / (pin[1] ** 2 + 1e-2)) < 2e-3
 
 
 def test_reference_streams_render(scene_case):
