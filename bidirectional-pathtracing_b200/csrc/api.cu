@@ -272,19 +272,21 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
   CK(cudaMemsetAsync(ctx->qctr, 0, 4 * sizeof(unsigned int), ctx->stream));
   const int threads = 128;
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 0), ctx->stream);
-  const int wtr = (ctx->spec & 1) ? ctx->traits : 0;
+  const bool lens = ctx->lens_radius > 0.0;   // thin lens: the generic build that carries the extension
+  const int wtr = lens ? BDPT_TRAIT_LENS : (ctx->spec & 1) ? ctx->traits : 0;
   if (ctx->sched) {
     const int g = ctx->sm_count * ctx->walk_ctas;
     // 6 CTAs/SM (80 registers, ~0.2 KB of spills) beats 4 CTAs at 101 registers by 6 %: the state machine is
     // latency-bound between votes.  BDPT_VARIANT=1 selects the unspilled build for comparison.
     const size_t shm = (size_t)J.ntop * 80;
-    if (ctx->variant == 1) k_walk_pt<16, 8, 4><<<g, threads, shm, ctx->stream>>>(J);
+    if (ctx->variant == 1 && !lens) k_walk_pt<16, 8, 4><<<g, threads, shm, ctx->stream>>>(J);
     else switch (wtr) {
       case 1: k_walk_pt<14, 6, 6, 1><<<g, threads, shm, ctx->stream>>>(J); break;
       case 2: k_walk_pt<14, 6, 6, 2><<<g, threads, shm, ctx->stream>>>(J); break;
       case 3: k_walk_pt<14, 6, 6, 3><<<g, threads, shm, ctx->stream>>>(J); break;
       case 4: k_walk_pt<14, 6, 6, 4><<<g, threads, shm, ctx->stream>>>(J); break;
       case 5: k_walk_pt<14, 6, 6, 5><<<g, threads, shm, ctx->stream>>>(J); break;
+      case BDPT_TRAIT_LENS: k_walk_pt<14, 6, 6, BDPT_TRAIT_LENS><<<g, threads, shm, ctx->stream>>>(J); break;
       default: k_walk_pt<14, 6, 6, 0><<<g, threads, shm, ctx->stream>>>(J); break;
     }
   } else {
@@ -295,6 +297,7 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
       case 3: k_walk<3><<<g, threads, 0, ctx->stream>>>(J); break;
       case 4: k_walk<4><<<g, threads, 0, ctx->stream>>>(J); break;
       case 5: k_walk<5><<<g, threads, 0, ctx->stream>>>(J); break;
+      case BDPT_TRAIT_LENS: k_walk<BDPT_TRAIT_LENS><<<g, threads, 0, ctx->stream>>>(J); break;
       default: k_walk<0><<<g, threads, 0, ctx->stream>>>(J); break;
     }
   }
@@ -307,7 +310,8 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
   J.seg_cap = (unsigned)(BDPT_CONNECT_NT * (J.m + 1) * (J.m + 1));
   J.chunk_cap = (unsigned)std::min<size_t>(ctx->cap_chunks, 0xffffffffu);
   const int ctr = (!TRACE && (ctx->spec & 2)) ? (ctx->traits & (BDPT_TRAIT_LAMBERT | BDPT_TRAIT_NOMF)) : 0;
-  if (ctr & BDPT_TRAIT_LAMBERT) launch_connect<TRACE, BDPT_TRAIT_LAMBERT>(ctx, J, cgrid, ctx->connect_minb ? ctx->connect_minb : 6);
+  if (lens) launch_connect<TRACE, BDPT_TRAIT_LENS>(ctx, J, cgrid, ctx->connect_minb ? ctx->connect_minb : 6);
+  else if (ctr & BDPT_TRAIT_LAMBERT) launch_connect<TRACE, BDPT_TRAIT_LAMBERT>(ctx, J, cgrid, ctx->connect_minb ? ctx->connect_minb : 6);
   else if (ctr & BDPT_TRAIT_NOMF) launch_connect<TRACE, BDPT_TRAIT_NOMF>(ctx, J, cgrid, ctx->connect_minb ? ctx->connect_minb : 6);
   else launch_connect<TRACE, 0>(ctx, J, cgrid, ctx->connect_minb ? ctx->connect_minb : 6);
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 2), ctx->stream);

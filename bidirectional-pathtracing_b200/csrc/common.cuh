@@ -99,6 +99,10 @@ struct alignas(16) Node8 {  // 80 bytes, see bvh8.h
 #define BDPT_TRAIT_TRIS 1      // every primitive is a triangle
 #define BDPT_TRAIT_LAMBERT 2   // every material is DiffuseBSDF or EmissionBSDF
 #define BDPT_TRAIT_NOMF 4      // no MicrofacetBSDF (implied by LAMBERT; used when LAMBERT does not hold)
+// ... and one that ADDS code: the thin-lens extension (bdpt_set_lens) lives only in the builds that carry this bit —
+// the generic build plus the lens — so that the pinhole renders the reference ships pay nothing for it (inlined into
+// every build it cost the walk kernel 2 %).
+#define BDPT_TRAIT_LENS 8
 
 struct DScene {
   const uint4* nodes;       // Node8 as 5 x uint4

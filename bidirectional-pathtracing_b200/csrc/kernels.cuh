@@ -127,7 +127,9 @@ struct WalkState {
 
 // New subpath: pinhole ray (raytrace_pixel, bidirection.cpp:517-524) or light emission
 // (sample_light_ray, :105-118).  Returns false if the index maps to no pixel.
+template <int TR = 0>
 __device__ inline bool walk_begin(const Job& J, unsigned i, WalkState& W, Trav& T) {
+  const bool lens = (TR & BDPT_TRAIT_LENS) && J.cam.lens_radius > 0.f;
   W.kind = i >= (unsigned)J.B ? 1 : 0;
   W.si = (int)i - W.kind * J.B;
   int x, y, sample;
@@ -138,13 +140,16 @@ __device__ inline bool walk_begin(const Job& J, unsigned i, WalkState& W, Trav& 
   f3 o, d;
   if (W.kind == 0) {
     float sx = W.rng.uniform(), sy = W.rng.uniform();
-    if (J.cam.lens_radius > 0.f) {   // thin lens (extension): two more draws, the eye subpath starts on the lens
+    if (lens) {   // thin lens (extension): two more draws, the eye subpath starts on the lens
       const float u1 = W.rng.uniform(), u2 = W.rng.uniform();
       camera_generate_ray_lens(J.cam, ((float)x + sx) / (float)J.cam.W, ((float)y + sy) / (float)J.cam.H, u1, u2, &o, &d);
     } else
     camera_generate_ray(J.cam, ((float)x + sx) / (float)J.cam.W, ((float)y + sy) / (float)J.cam.H, &o, &d);
     W.prev_n = d; W.alpha = mk3(1.f); W.prev_pdf = 1.f;
     W.pdfeval_prev = 1.f; W.D_prev = 1.f; W.S_prev = 0.f;
+    if (lens) {   // thin lens: the lens point can also be reached by a light subpath (t = 0), density 1 / lens area
+      W.S_prev = 1.f; W.D_prev = 1.0f / (BDPT_PI * J.cam.lens_radius * J.cam.lens_radius);
+    }
     T.begin(o, d, J.cam.nclip, J.cam.fclip);
   } else {
     int li = W.rng.pick(J.sc.n_lights);
@@ -164,6 +169,53 @@ __device__ inline bool walk_begin(const Job& J, unsigned i, WalkState& W, Trav& 
   return true;
 }
 
+// Thin lens: the camera vertex of an eye subpath is not stored; its lens point is re-drawn from the eye stream
+// (walk_begin: two raster draws, then the two lens draws).
+__device__ inline f3 lens_vertex(const Job& J, unsigned long long pix, unsigned long long sample) {
+  Rng re;
+  re.begin(J.seed, pix, sample, 0u);
+  re.uniform(); re.uniform();
+  const float u1 = re.uniform(), u2 = re.uniform();
+  const f3 lc = lens_point(J.cam, u1, u2);
+  return J.cam.pos + lc.x * J.cam.c2w_x + lc.y * J.cam.c2w_y;
+}
+
+// Thin lens, strategy t = 0 (extension; oracle/bdpt_oracle.cpp splat_lens_hit): the segment o + t d of a LIGHT subpath
+// crosses the lens before it reaches a surface.  C = alpha at the lens * We / (lens area * cos at the lens), weighted
+// against t' = 1 (the camera samples this lens point and connects) and the rest of the light-side chain; it goes to the
+// light image like a t = 1 splat.  The lens is no occluder: the walk goes on to its surface hit.
+__device__ inline void lens_strategy(const Job& J, const WalkState& W, f3 o, f3 d, float tmax) {
+  const DCamera& c = J.cam;
+  const int s = W.j - 1;
+  if (J.only_t >= 0 && (J.only_t != 0 || J.only_s != s)) return;
+  const f3 oc = o - c.pos;
+  const f3 ocl = mk3(dot(c.w2c_r0, oc), dot(c.w2c_r1, oc), dot(c.w2c_r2, oc));
+  const f3 dcl = mk3(dot(c.w2c_r0, d), dot(c.w2c_r1, d), dot(c.w2c_r2, d));
+  if (!(dcl.z > 0.f)) return;                       // must arrive from the front
+  const float tl = -ocl.z / dcl.z;
+  if (!(tl > BDPT_EPS_F && tl < tmax)) return;
+  const float lx = ocl.x + dcl.x * tl, ly = ocl.y + dcl.y * tl;
+  if (lx * lx + ly * ly >= c.lens_radius * c.lens_radius) return;
+  f3 eye, wi; float dist, cam_dir_pdf; int ex, ey;
+  const float We = camera_sample_ray_pdf_lens(c, o, mk3(lx, ly, 0.f), &eye, &wi, &dist, &cam_dir_pdf, &ex, &ey);
+  if (!(ex >= 0 && ey >= 0 && ex < c.W && ey < c.H)) return;
+  const float A = BDPT_PI * c.lens_radius * c.lens_radius;
+  const float cos_prev = fabsf(dot(W.prev_n, d));
+  const float cos_u = dcl.z / norm(dcl);
+  const f3 contrib = W.alpha * W.prev_f * (cos_prev / W.prev_pdf) * (We / (A * cos_u));
+  if (!(norm(contrib) > BDPT_EPS_F)) return;
+  float w = 1.f;
+  if (!J.no_mis) {
+    const float g0 = cos_prev / (dist * dist);
+    const float ratio1 = (1.0f / A) / (W.pdfeval_prev * g0);          // p_1 / p_0
+    const float r_s = cam_dir_pdf * g0 / W.D_prev;
+    const double winv = 1.0 + (double)mis_pow(J, ratio1) * ((double)((s >= 2 && W.delta_prev) ? 0.f : 1.f) + (double)mis_pow(J, r_s) * (double)W.S_prev);
+    w = (float)(1.0 / winv);
+    if (!(w >= 0.f)) w = 0.f;
+  }
+  splat_rgb(J.acc_light + (size_t)(ey * c.W + ex), contrib.x * w, contrib.y * w, contrib.z * w);
+}
+
 // The traversal of the current ray finished: store the vertex (if any) and sample the next ray
 // (body of the while loop of prepare_bidirectional_subpath, bidirection.cpp:44-101).
 // Returns true if the subpath continues (T holds the next ray), false if it ended.
@@ -171,6 +223,7 @@ template <int TR = 0>
 __device__ inline bool walk_shade(const Job& J, WalkState& W, Trav& T) {
   const DScene& sc = J.sc;
   const f3 o = T.o, d = T.d;
+  if ((TR & BDPT_TRAIT_LENS) && W.kind == 1 && J.cam.lens_radius > 0.f) lens_strategy(J, W, o, d, T.hit.leaf < 0 ? INFINITY : T.hit.t);
   if (T.hit.leaf < 0) {
     if (sc.env_light < 0 || W.kind != 0) return false;   // (a LIGHT subpath's vertex on an emitter carries nothing: f = 0)
     // The ray leaves the scene: it meets the environment's sphere (shading.cuh, "environment light"), whose surface
@@ -247,13 +300,13 @@ __device__ inline void walk_end(const Job& J, const WalkState& W) {
 
 // One subpath per lane, start to end.  Used for scenes whose BVH has at most 8 nodes (nothing diverges there).
 template <int TR = 0>
-__global__ void __launch_bounds__(128) k_walk(const Job J) {
+__global__ void __launch_bounds__(128) k_walk(const __grid_constant__ Job J) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;   // whole warps are in or out: 2B is a multiple of 32
   if (i >= 2u * (unsigned)J.B) return;
   WalkState W; Trav T;
   uint2 stack[BDPT_STACK];
   unsigned nrays = 0;
-  if (walk_begin(J, i, W, T)) {
+  if (walk_begin<TR>(J, i, W, T)) {
     for (;;) {
       while (!T.template step<false, TR>(J.sc, stack)) {}
       nrays++;
@@ -298,7 +351,7 @@ __device__ inline Vtx load_vtx(const Job& J, int kind, int j, int si) {
 // and of the same or neighbouring samples (their vertex loads coalesce), there is no loop-carried state, and
 // each vertex record is fetched from DRAM by exactly one block.
 template <bool TRACE, int MINB, int TR = 0>
-__global__ void __launch_bounds__(BDPT_CONNECT_NT, MINB) k_connect(const Job J) {
+__global__ void __launch_bounds__(BDPT_CONNECT_NT, MINB) k_connect(const __grid_constant__ Job J) {
   constexpr int NT = BDPT_CONNECT_NT, NW = NT / 32;
   __shared__ unsigned s_pre[5][NT];    // exclusive prefix of the per-sample strategy counts, per kind
   __shared__ unsigned s_wsum[5][NW];
@@ -307,6 +360,7 @@ __global__ void __launch_bounds__(BDPT_CONNECT_NT, MINB) k_connect(const Job J) 
   __shared__ unsigned s_len[NT];       // nE | nL << 8
   __shared__ unsigned s_qn;            // entries of this block's queue segment
   const DScene& sc = J.sc;
+  const bool lens_on = (TR & BDPT_TRAIT_LENS) && J.cam.lens_radius > 0.f;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int si0 = blockIdx.x * NT;
   const f3 zero = mk3(0.f);
@@ -445,6 +499,16 @@ __global__ void __launch_bounds__(BDPT_CONNECT_NT, MINB) k_connect(const Job J) 
               tail = mis_pow(J, dp * gp / P.D) * P.S;
             }
           }
+          if (t == 2 && lens_on) {
+            // thin lens: the emitter could have emitted straight onto the lens point this eye subpath started from
+            // (t' = 0)
+            const f3 wv = lens_vertex(J, (unsigned long long)pix_own, (unsigned long long)s_smp[j]) - E.pos;
+            const float d2 = dot(wv, wv);
+            float pp, dp;
+            light_sample_pdf(sc, L, E.pos, -E.wo, &pp, &dp);
+            const float gp = fabsf(dot(E.n, wv * rsqrtf(d2))) / d2;     // (the camera vertex's cosine is 1 by convention)
+            tail = mis_pow(J, dp * gp * (BDPT_PI * J.cam.lens_radius * J.cam.lens_radius));
+          }
           double winv = 1.0 + (double)mis_pow(J, r_t) * ((double)(delta_prev ? 0.f : 1.f) + (double)tail);
           w = J.no_mis ? 1.f : (float)(1.0 / winv);
           if (!(w >= 0.f)) w = 0.f;
@@ -473,7 +537,7 @@ __global__ void __launch_bounds__(BDPT_CONNECT_NT, MINB) k_connect(const Job J) 
         if (t == 1) {
           f3 wi; float dd;
           float We;
-          if (J.cam.lens_radius > 0.f) {   // thin lens (extension): a fresh point of the lens, stream 64 + s
+          if (lens_on) {   // thin lens (extension): a fresh point of the lens, stream 64 + s
             Rng r2;
             r2.begin(J.seed, (unsigned long long)pix_own, (unsigned long long)s_smp[j], 64u + (uint32_t)s);
             const float u1 = r2.uniform(), u2 = r2.uniform();
@@ -512,13 +576,19 @@ __global__ void __launch_bounds__(BDPT_CONNECT_NT, MINB) k_connect(const Job J) 
         float P_le = s == 1 ? ls_dir_pdf : bsdf_pdf_mis_z(ML, woLz, cLz, hxyL) * Lv.q;
         float r_t = P_le * g / E.D;
         float S_t = E.S;
-        if (ME.type == BDPT_MAT_MICROFACET && t >= 3) {
+        if (ME.type == BDPT_MAT_MICROFACET && (t >= 3 || lens_on)) {
           // wo-dependent density: the chain factor next to the connection cannot come from the walk's cache
-          Vtx P = load_vtx(J, 0, t - 1, sj);
+          Vtx P;
+          if (t >= 3) P = load_vtx(J, 0, t - 1, sj);
+          else {   // thin lens: the camera vertex (walk_begin: density 1 / lens area, S = 1, cosine 1 by convention)
+            P.pos = lens_vertex(J, (unsigned long long)pix_own, (unsigned long long)s_smp[j]);
+            P.n = E.wo; P.mat = -1; P.S = 1.f;
+            P.D = 1.0f / (BDPT_PI * J.cam.lens_radius * J.cam.lens_radius);
+          }
           f3 wv = P.pos - E.pos; float d2 = dot(wv, wv);
           float gp = fabsf(woEz * dot(wv * rsqrtf(d2), P.n)) / d2;
           float R = bsdf_pdf_mis_z(ME, cEz, woEz, hxyE) * E.q * gp / P.D;
-          S_t = clampS((type_is_delta(mat_type<TR>(sc, P.mat)) ? 0.f : 1.f) + (P.S > 0.f ? mis_pow(J, R) * P.S : 0.f));
+          S_t = clampS(((t >= 3 && type_is_delta(mat_type<TR>(sc, P.mat))) ? 0.f : 1.f) + (P.S > 0.f ? mis_pow(J, R) * P.S : 0.f));
         }
         winv += (double)mis_pow(J, r_t) * (double)S_t;
       }
@@ -547,6 +617,11 @@ __global__ void __launch_bounds__(BDPT_CONNECT_NT, MINB) k_connect(const Job J) 
         float gp = fabsf(cosA * dot(wd, mk3(lb.x, lb.y, lb.z))) / d2;
         float r_s = P_el * gp / lb.w;
         winv += (double)mis_pow(J, r_s);
+      }
+      if (t == 1 && lens_on) {
+        // thin lens: the light vertex could also have scattered onto this very lens point (t' = 0)
+        const float P_le = s == 1 ? ls_dir_pdf : bsdf_pdf_mis_z(ML, woLz, cLz, hxyL) * Lv.q;
+        winv += (double)mis_pow(J, P_le * g * (BDPT_PI * J.cam.lens_radius * J.cam.lens_radius));
       }
       w = J.no_mis ? 1.f : (float)(1.0 / winv);
       if (!(w >= 0.f)) w = 0.f;  // NaN guard
@@ -738,7 +813,7 @@ __global__ void __launch_bounds__(128, MINB) k_shadow_pt(const Job J) {
 
 // phase: 0 = empty (wants a subpath), 1 = traversing, 2 = traversal finished (wants shading)
 template <int SHADE_THRESHOLD, int FETCH_THRESHOLD, int MINB = 4, int TR = 0>
-__global__ void __launch_bounds__(128, MINB) k_walk_pt(const Job J) {
+__global__ void __launch_bounds__(128, MINB) k_walk_pt(const __grid_constant__ Job J) {
   extern __shared__ uint4 top[];
   stage_top_nodes(J, top);
   Trav T;
@@ -763,7 +838,7 @@ __global__ void __launch_bounds__(128, MINB) k_walk_pt(const Job J) {
     const unsigned empty = __ballot_sync(0xffffffffu, phase == 0);
     if (empty != 0u && !wf.exhausted && (__popc(empty) >= FETCH_THRESHOLD || __ballot_sync(0xffffffffu, phase == 1) == 0u)) {
       unsigned my = warp_fetch(J.qctr + 3, total, 128u, phase == 0, wf);
-      if (my != BDPT_NONE && walk_begin(J, my, W, T)) phase = 1;
+      if (my != BDPT_NONE && walk_begin<TR>(J, my, W, T)) phase = 1;
     }
     if (__ballot_sync(0xffffffffu, phase != 0) == 0u && wf.exhausted) break;
     if (phase == 1) {

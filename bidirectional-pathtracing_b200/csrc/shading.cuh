@@ -435,7 +435,7 @@ __device__ inline void camera_generate_ray(const DCamera& c, float x, float y, f
 // lens (that function, verbatim) and a light-tracing connection (t = 1) goes through a fresh point of the lens: the
 // formulas of sample_ray_pdf with the lens point in place of the pinhole and the angle of the actual ray; the raster
 // position is that of the sensor sample whose rays converge where this ray meets the plane of focus.  t = 0 (a light
-// subpath that hits the lens) is not a strategy here.
+// subpath that crosses the lens) is kernels.cuh's lens_strategy.
 __device__ inline f3 lens_point(const DCamera& c, float rnd_r, float rnd_u) {   // camera space, z = 0
   float sn, cs;
   sincos_2pi(rnd_u, &sn, &cs);

@@ -108,7 +108,9 @@ int bdpt_set_frame(BdptContext* ctx, int width, int height);
  * raytraced_renderer.cpp:141-142).  The reference's BDPT renders through a pinhole whatever they are (it calls
  * generate_ray, bidirection.cpp:524), which is lens_radius = 0, the default.  lens_radius > 0 is an
  * extension: eye subpaths start on the lens (Camera::generate_ray_for_thin_lens, camera_lens.cpp:22-43) and t = 1
- * connections go through a sampled point of it; there is no t = 0 strategy. */
+ * connections go through a sampled point of it; a light subpath that crosses the lens is the t = 0 strategy (splatted to
+ * the light image), and every MIS weight gains that alternative.  Behaviour defined by oracle/bdpt_oracle.cpp
+ * (splat_lens_hit, mis_weight); lens renders use the generic kernel build (BDPT_TRAIT_LENS). */
 int bdpt_set_lens(BdptContext* ctx, double lens_radius, double focal_distance);
 /* Cell render, the reference's `-p x y dx dy` (RaytracedRenderer::render_to_file with a cell, raytraced_renderer.cpp:
  * 330-347, tile queue over the cell :301-319): later bdpt_render calls sample only the pixels of [x, x+dx) x [y, y+dy)

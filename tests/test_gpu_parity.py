@@ -17,6 +17,7 @@ import numpy as np
 import pytest
 
 from conftest import ALL_SCENES, GOLDEN, load_scene
+from bdpt import flatscene as fs
 
 pytestmark = pytest.mark.gpu
 
@@ -461,10 +462,12 @@ def test_environment_render_matches_oracle(api, O, kind, m, envmap):
 
 
 # ---------------------------------------------------------------------------- thin lens (extension)
-@pytest.mark.parametrize("name,radius,focus", [("CBspheres", 0.1, 4.5), ("CBspheres_lambertian", 0.3, 3.0), ("CBempty", 0.2, 4.0)])
+@pytest.mark.parametrize("name,radius,focus", [("CBspheres", 0.1, 4.5), ("CBspheres_lambertian", 0.3, 3.0), ("CBempty", 0.2, 4.0),
+                                               ("CBbunny_microfacet_cu", 0.2, 4.5)])
 def test_thin_lens_render_matches_oracle(api, O, name, radius, focus):
     """bdpt_set_lens: eye subpaths from Camera::generate_ray_for_thin_lens, t = 1 connections through a sampled lens
-    point — the CUDA path against the oracle with the same random numbers (image and single samples)."""
+    point, t = 0 where a light subpath crosses the lens — the CUDA path against the oracle with the same random numbers
+    (image and single samples; the microfacet bunny exercises the wo-dependent chain factor at the camera vertex)."""
     W, H, ns, m = 64, 48, 8, 4
     R = make_renderer(api, name, W, H, ns_aa=ns, max_ray_depth=m, seed=17)
     R.set_lens(radius, focus)
@@ -492,6 +495,37 @@ def test_thin_lens_render_matches_oracle(api, O, name, radius, focus):
     assert n_strat > 200 and n_bad <= 0.04 * n_strat, (n_bad, n_strat)
 
 
+def wide_lens_scene(name="CBempty"):
+    sc = load_scene(name)
+    cam = sc.camera.copy()
+    cam["screen_dist"] = cam["screen_dist"] / 10        # the whole box in view at 48 x 36
+    return fs.FlatScene(cam, sc.materials, sc.lights, sc.prims), float(sc.camera[0]["pos"][2] + 1.0)
+
+
+def test_thin_lens_t0_strategy(api, O):
+    """Strategy t = 0 (extension): a light subpath's segment crosses the lens.  (a) the CUDA path's (0, s) images equal
+    the oracle's with the same random numbers, weighted and unweighted; (b) the known answer — unweighted, (0, s) and
+    (1, s) estimate the same image, so their totals agree."""
+    W, H, m = 48, 36, 3
+    sc, focus = wide_lens_scene()
+    orc = O.Oracle(sc, W, H); orc.set_lens(0.5, focus)
+    for s_ in (1, 2, 3):
+        for no_mis in (0, 1):
+            R = api.Renderer(0, ns_aa=64, max_ray_depth=m, seed=5, no_mis=bool(no_mis))
+            R.set_scene(sc); R.set_frame_size(W, H); R.set_lens(0.5, focus); R.render(strategy=(0, s_))
+            g = R.framebuffer(2).astype(np.float64)
+            o = orc.render(64, m, rng_mode=1, seed=5, threads=8, no_mis=no_mis, strategy=(0, s_))[2]
+            assert R.framebuffer(1).max() == 0 and o.sum() > 0
+            assert abs(g.sum() - o.sum()) <= 2e-3 * o.sum() and relmse(g, o) <= 1e-3, (s_, no_mis, g.sum(), o.sum())
+    for s_, tol in ((2, 0.01), (3, 0.01)):
+        tot = []
+        for t_ in (0, 1):
+            R = api.Renderer(0, ns_aa=16384, max_ray_depth=m, seed=6 + t_, no_mis=True)
+            R.set_scene(sc); R.set_frame_size(W, H); R.set_lens(0.5, focus); R.render(strategy=(t_, s_))
+            tot.append(float(R.framebuffer(2).astype(np.float64).sum()))
+        assert abs(tot[0] - tot[1]) < tol * tot[1], (s_, tot)
+
+
 def test_thin_lens_known_answers(api):
     """A diffuse wall in the plane of focus looks the same through any lens: CBempty at 48 x 36 shows only the box's back
     wall (z = -1, 5.802 from the camera along the view axis); focused there, the eye image equals the pinhole's up to
@@ -508,6 +542,7 @@ def test_thin_lens_known_answers(api):
         eye = L.framebuffer(1)
         assert abs(eye.mean() - pin[1].mean()) < 2e-3 * pin[1].mean(), radius
         assert relmse(eye, pin[1]) < 3e-4, radius
+        assert abs(L.framebuffer(0).mean() - pin[0].mean()) < 3e-3 * pin[0].mean(), radius   # all strategies, t = 0 included
     D = make_renderer(api, name, W, H, ns_aa=ns, max_ray_depth=m, seed=3); D.set_lens(0.3, 1.0); D.render()
     assert relmse(D.framebuffer(1), pin[1]) > 3e-4        # out of focus it is another image
     with pytest.raises(api.BdptError, match="lens"):

@@ -11,6 +11,7 @@ import pytest
 
 from conftest import ALL_SCENES, GOLDEN, load_scene
 from oracle import oracle as O
+from bdpt import flatscene as fs
 
 
 @pytest.fixture(scope="module", params=ALL_SCENES)
@@ -170,6 +171,30 @@ def test_thin_lens_known_answers():
         img = lens.render(ns, m, rng_mode=1, seed=2, threads=8)
         assert abs(img[1].mean() - pin[1].mean()) < 5e-3 * pin[1].mean()
         assert np.mean((img[1] - pin[1]) ** 2 / (pin[1] ** 2 + 1e-2)) < 2e-3
+
+
+def test_thin_lens_t0_strategy_known_answers():
+    """Extension, strategy t = 0 (a light subpath crosses the lens itself).  Unweighted, (t = 0, s) and (t = 1, s)
+    estimate the same image — the paths of s light vertices seen directly through the lens — so their light images
+    agree in total; and with MIS the in-focus wall still looks the same through the lens as through the pinhole, now on
+    the SUM image (all strategies), not only the eye image."""
+    W, H, m = 48, 36, 3
+    sc = load_scene("CBempty")
+    focus = float(sc.camera[0]["pos"][2] + 1.0)
+    wide = sc.camera.copy(); wide["screen_dist"] = wide["screen_dist"] / 10     # the whole box in view (SURVEY F9)
+    lens = O.Oracle(fs.FlatScene(wide, sc.materials, sc.lights, sc.prims), W, H); lens.set_lens(0.5, focus)
+    for s_, tol in ((1, 0.06), (2, 0.02), (3, 0.02)):
+        t0 = lens.render(1024, m, rng_mode=1, seed=3, threads=8, no_mis=1, strategy=(0, s_))
+        t1 = lens.render(1024, m, rng_mode=1, seed=4, threads=8, no_mis=1, strategy=(1, s_))
+        assert t0[1].max() == 0 and t1[1].max() == 0          # both splat the light image only
+        assert t0[2].sum() > 0 and abs(t0[2].sum() - t1[2].sum()) < tol * t1[2].sum(), (s_, t0[2].sum(), t1[2].sum())
+    lens = O.Oracle(sc, W, H); lens.set_lens(0.5, focus)
+    ns = 256
+    pin = O.Oracle(sc, W, H).render(ns, m, rng_mode=1, seed=1, threads=8)
+    img = lens.render(ns, m, rng_mode=1, seed=2, threads=8)
+    assert abs(img[0].mean() - pin[0].mean()) < 1e-2 * pin[0].mean()
+    w0 = lens.render(ns, m, rng_mode=1, seed=2, threads=8, strategy=(0, 2))
+    assert w0[2].sum() > 0                                   # the weighted t = 0 strategy is part of that sum
 
 
 def test_reference_streams_render(scene_case):
