@@ -31,7 +31,11 @@ BDPT_HD inline uint64_t ploc_morton(const float* c, const float* clo, const floa
   uint32_t q[3];
   for (int a = 0; a < 3; a++) {
     const float ext = chi[a] - clo[a];
+#ifdef __CUDA_ARCH__   // (the library is built with -prec-div=false; the key must be the host restatement's bit for bit)
+    float u = ext > 0.f ? __fdiv_rn(c[a] - clo[a], ext) : 0.f;
+#else
     float u = ext > 0.f ? (c[a] - clo[a]) / ext : 0.f;
+#endif
     u = u < 0.f ? 0.f : u > 1.f ? 1.f : u;
     double s = (double)u * 2097151.0;
     q[a] = (uint32_t)s;

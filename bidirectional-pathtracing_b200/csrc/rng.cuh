@@ -1,4 +1,6 @@
-// rng.cuh — counter-keyed random streams.  One PCG-XSH-RR 64/32 stream per
+// rng.cuh — counter-keyed random streams.  One PCG-RXS-M-XS 32/32 stream (32-bit LCG state, its increment and start
+// taken from a 64-bit hash of the key: 7 integer instructions a draw where the 64/32 generator of round 1 took ~16 —
+// 64-bit multiplies are four IMADs on the GPU — walk -2.3 %; a stream here is at most a few dozen draws) per
 // (seed, pixel, sample index, stream id); the fp64 oracle (oracle/bdpt_oracle.cpp, Rng,
 // rng_mode 1) implements the identical generator so both sides draw the same numbers.
 //
@@ -20,23 +22,18 @@ __host__ __device__ inline uint64_t mix64(uint64_t z) {  // splitmix64 finaliser
 }
 
 struct Rng {
-  uint64_t state, inc;
-
+  uint32_t state, inc;
   __host__ __device__ inline void begin(uint64_t seed, uint64_t pixel, uint64_t sample, uint32_t stream) {
     uint64_t h = mix64(seed ^ mix64(pixel * 0x9E3779B97F4A7C15ull + sample) ^
                        (0xD1B54A32D192ED03ull * (uint64_t)(stream + 1)));
-    inc = (mix64(h) << 1) | 1ull;
-    state = h;
+    state = (uint32_t)h; inc = (uint32_t)(h >> 32) | 1u;   // (an odd increment: full period 2^32)
   }
   __host__ __device__ inline uint32_t next() {
-    uint64_t old = state;
-    state = old * 6364136223846793005ull + inc;
-    uint32_t xorshifted = (uint32_t)(((old >> 18u) ^ old) >> 27u);
-    uint32_t rot = (uint32_t)(old >> 59u);
-    return (xorshifted >> rot) | (xorshifted << ((32 - rot) & 31));
+    uint32_t old = state;
+    state = old * 747796405u + inc;
+    uint32_t word = ((old >> ((old >> 28u) + 4u)) ^ old) * 277803737u;
+    return (word >> 22u) ^ word;
   }
-  // (k + 0.5) * 2^-23, k = top 23 bits: strictly inside (0,1) and exactly representable in fp32,
-  // so the fp64 oracle and the fp32 kernels see the same value.
   __host__ __device__ inline float uniform() { return ((float)(next() >> 9) + 0.5f) * (1.0f / 8388608.0f); }
   __host__ __device__ inline int pick(int n) {
     int k = (int)(uniform() * (float)n);

@@ -517,10 +517,11 @@ def test_thin_lens_t0_strategy(api, O):
             o = orc.render(64, m, rng_mode=1, seed=5, threads=8, no_mis=no_mis, strategy=(0, s_))[2]
             assert R.framebuffer(1).max() == 0 and o.sum() > 0
             assert abs(g.sum() - o.sum()) <= 2e-3 * o.sum() and relmse(g, o) <= 1e-3, (s_, no_mis, g.sum(), o.sum())
-    for s_, tol in ((2, 0.01), (3, 0.01)):
+    # (a (0, s) total at 65536 spp has a standard deviation of ~0.4 %: 2 % at 2048 spp measured with the oracle)
+    for s_, tol in ((2, 0.015), (3, 0.015)):
         tot = []
         for t_ in (0, 1):
-            R = api.Renderer(0, ns_aa=16384, max_ray_depth=m, seed=6 + t_, no_mis=True)
+            R = api.Renderer(0, ns_aa=65536, max_ray_depth=m, seed=6 + t_, no_mis=True)
             R.set_scene(sc); R.set_frame_size(W, H); R.set_lens(0.5, focus); R.render(strategy=(t_, s_))
             tot.append(float(R.framebuffer(2).astype(np.float64).sum()))
         assert abs(tot[0] - tot[1]) < tol * tot[1], (s_, tot)
