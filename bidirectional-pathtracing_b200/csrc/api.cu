@@ -636,28 +636,8 @@ int bdpt_upload_scene(BdptContext* ctx, const BdptCamera* camera, const BdptMate
     // leaf-ordered primitive + shading records
     std::vector<float4> hp(3 * (size_t)std::max<uint32_t>(n_prims, 1)), hs(3 * (size_t)std::max<uint32_t>(n_prims, 1));
     std::vector<double> h64(10 * (size_t)std::max<uint32_t>(n_prims, 1), 0.0);
-    for (size_t k = 0; k < bvh.prim_order.size(); k++) {
-      uint32_t id = bvh.prim_order[k];
-      const BdptPrim& p = prims[id];
-      const double* d = p.data;
-      for (int a = 0; a < 9; a++) h64[10 * k + a] = d[a];  // triangle p1 p2 p3 / sphere centre, radius
-      if (p.type == BDPT_PRIM_TRIANGLE) {
-        float v0[3], v1[3], v2[3];
-        for (int a = 0; a < 3; a++) { v0[a] = (float)d[a]; v1[a] = (float)d[3 + a]; v2[a] = (float)d[6 + a]; }
-        hp[3 * k + 0] = make_float4(v0[0], v0[1], v0[2], ibits((int)id));
-        hp[3 * k + 1] = make_float4(v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2], ibits(p.material));
-        hp[3 * k + 2] = make_float4(v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2], 0.f);
-        hs[3 * k + 0] = make_float4((float)d[9], (float)d[10], (float)d[11], 0.f);
-        hs[3 * k + 1] = make_float4((float)d[12], (float)d[13], (float)d[14], 0.f);
-        hs[3 * k + 2] = make_float4((float)d[15], (float)d[16], (float)d[17], 0.f);
-      } else {
-        float r = (float)d[3];
-        hp[3 * k + 0] = make_float4((float)d[0], (float)d[1], (float)d[2], ibits((int)id));
-        hp[3 * k + 1] = make_float4(r, (float)(d[3] * d[3]), 0.f, ibits(p.material | (int)0x80000000));
-        hp[3 * k + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
-        hs[3 * k + 0] = hs[3 * k + 1] = hs[3 * k + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
+    for (size_t k = 0; k < bvh.prim_order.size(); k++)
+      make_leaf_record(prims[bvh.prim_order[k]], bvh.prim_order[k], hp.data() + 3 * k, hs.data() + 3 * k, h64.data() + 10 * k);
     CK(ensure((void**)&ctx->d_nodes, &ctx->cap_scene[0], bvh.nodes.size() * sizeof(uint32_t)));
     CK(ensure((void**)&ctx->d_prims, &ctx->cap_scene[1], hp.size() * sizeof(float4)));
     CK(ensure((void**)&ctx->d_shading, &ctx->cap_scene[2], hs.size() * sizeof(float4)));

@@ -244,30 +244,55 @@ __global__ void k_bvh_emit_level(DevTree T, const uint8_t* split, const uint8_t*
   }
 }
 
-// ---- leaf-ordered records the traversal and shading read (layouts: api.cu, bdpt_upload_scene)
+// ---- leaf-ordered records the traversal and shading read (one definition for the device build and the host one)
+//   prims   3 x float4 per leaf slot.  Triangle: the three rows of the affine map world -> (u, v, w) with
+//           p = v0 + u e1 + v e2 + w n, n = e1 x e2 (the "unit triangle" form of Woop et al.; computed in fp64): a ray test
+//           is 5 three-term dot products and one reciprocal instead of Moller-Trumbore's two cross products and four.
+//           A degenerate triangle gets zero rows (never hit, as in the reference: triangle.cpp:57-95 divides by 0 and
+//           every comparison with the NaN fails).  Sphere: {centre, r^2}, -, {0, 0, 0, NaN} (the NaN is the type tag).
+//   shading 3 x float4: the vertex normals; .w of the first two: primitive id in build_accel order, material
+//           (| sign bit for a sphere)
+//   prims64 10 doubles: the fp64 geometry finish_hit re-intersects the winner with
+__host__ __device__ inline void make_leaf_record(const BdptPrim& p, uint32_t id, float4* hp, float4* hs, double* g) {
+  const double* d = p.data;
+  for (int a = 0; a < 9; a++) g[a] = d[a];
+  g[9] = 0.0;
+  union { int i; float f; } idb, matb;
+  idb.i = (int)id;
+  if (p.type == BDPT_PRIM_TRIANGLE) {
+    matb.i = p.material;
+    const double e1[3] = {d[3] - d[0], d[4] - d[1], d[5] - d[2]}, e2[3] = {d[6] - d[0], d[7] - d[1], d[8] - d[2]};
+    const double n[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+    const double det = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+    double R[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+    if (det > 0.0 && det == det && 1.0 / det < 1e300) {
+      const double inv = 1.0 / det;
+      R[0][0] = (e2[1] * n[2] - e2[2] * n[1]) * inv; R[0][1] = (e2[2] * n[0] - e2[0] * n[2]) * inv; R[0][2] = (e2[0] * n[1] - e2[1] * n[0]) * inv;
+      R[1][0] = (n[1] * e1[2] - n[2] * e1[1]) * inv; R[1][1] = (n[2] * e1[0] - n[0] * e1[2]) * inv; R[1][2] = (n[0] * e1[1] - n[1] * e1[0]) * inv;
+      R[2][0] = n[0] * inv; R[2][1] = n[1] * inv; R[2][2] = n[2] * inv;
+      for (int r = 0; r < 3; r++) R[r][3] = -(R[r][0] * d[0] + R[r][1] * d[1] + R[r][2] * d[2]);
+    }
+    for (int r = 0; r < 3; r++) hp[r] = make_float4((float)R[r][0], (float)R[r][1], (float)R[r][2], (float)R[r][3]);
+    hs[0] = make_float4((float)d[9], (float)d[10], (float)d[11], idb.f);
+    hs[1] = make_float4((float)d[12], (float)d[13], (float)d[14], matb.f);
+    hs[2] = make_float4((float)d[15], (float)d[16], (float)d[17], 0.f);
+  } else {
+    matb.i = p.material | (int)0x80000000;
+    union { unsigned u; float f; } nan; nan.u = 0x7fc00000u;
+    hp[0] = make_float4((float)d[0], (float)d[1], (float)d[2], (float)(d[3] * d[3]));
+    hp[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    hp[2] = make_float4(0.f, 0.f, 0.f, nan.f);
+    hs[0] = make_float4(0.f, 0.f, 0.f, idb.f);
+    hs[1] = make_float4(0.f, 0.f, 0.f, matb.f);
+    hs[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
 __global__ void k_bvh_records(const BdptPrim* prims, const uint32_t* prim_order, int n, float4* hp, float4* hs, double* h64) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const uint32_t id = prim_order[k];
-  const BdptPrim& p = prims[id];
-  const double* d = p.data;
-  double* g = h64 + 10 * (size_t)k;
-  for (int a = 0; a < 9; a++) g[a] = d[a];
-  g[9] = 0.0;
-  if (p.type == BDPT_PRIM_TRIANGLE) {
-    const float v0[3] = {(float)d[0], (float)d[1], (float)d[2]}, v1[3] = {(float)d[3], (float)d[4], (float)d[5]}, v2[3] = {(float)d[6], (float)d[7], (float)d[8]};
-    hp[3 * (size_t)k + 0] = make_float4(v0[0], v0[1], v0[2], __int_as_float((int)id));
-    hp[3 * (size_t)k + 1] = make_float4(v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2], __int_as_float(p.material));
-    hp[3 * (size_t)k + 2] = make_float4(v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2], 0.f);
-    hs[3 * (size_t)k + 0] = make_float4((float)d[9], (float)d[10], (float)d[11], 0.f);
-    hs[3 * (size_t)k + 1] = make_float4((float)d[12], (float)d[13], (float)d[14], 0.f);
-    hs[3 * (size_t)k + 2] = make_float4((float)d[15], (float)d[16], (float)d[17], 0.f);
-  } else {
-    hp[3 * (size_t)k + 0] = make_float4((float)d[0], (float)d[1], (float)d[2], __int_as_float((int)id));
-    hp[3 * (size_t)k + 1] = make_float4((float)d[3], (float)(d[3] * d[3]), 0.f, __int_as_float(p.material | (int)0x80000000));
-    hp[3 * (size_t)k + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
-    hs[3 * (size_t)k + 0] = hs[3 * (size_t)k + 1] = hs[3 * (size_t)k + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+  make_leaf_record(prims[id], id, hp + 3 * (size_t)k, hs + 3 * (size_t)k, h64 + 10 * (size_t)k);
 }
 
 }  // namespace bdpt

@@ -106,8 +106,8 @@ struct alignas(16) Node8 {  // 80 bytes, see bvh8.h
 
 struct DScene {
   const uint4* nodes;       // Node8 as 5 x uint4
-  const float4* prims;      // leaf-ordered primitive records, 3 x float4 each
-  const float4* shading;    // leaf-ordered shading normals n1,n2,n3, 3 x float4 each
+  const float4* prims;      // leaf-ordered primitive records, 3 x float4 each (layouts: bvh_gpu.cuh, make_leaf_record)
+  const float4* shading;    // leaf-ordered shading normals n1,n2,n3, 3 x float4 each; .w: primitive id, material, -
   const double* prims64;    // leaf-ordered fp64 geometry, 10 doubles each: triangle p1 p2 p3 (+pad) / sphere c, r
   const float4* materials;  // DMaterial as 5 x float4
   const float4* lights;     // DLight as 5 x float4

@@ -34,29 +34,33 @@ __device__ inline float qbyte(uint32_t w, int k, uint32_t bias_bits) {   // bias
   return __uint_as_float(__byte_perm(w, bias_bits, 0x7504u + ((uint32_t)k << 4)));
 }
 
-// Intersect one leaf primitive; returns true and shrinks tmax on an accepted hit.
+// Intersect one leaf primitive; returns true and shrinks tmax on an accepted hit.  (Record layouts: bvh_gpu.cuh,
+// make_leaf_record.)
 template <int TR = 0>
 __device__ inline bool intersect_prim(const float4* __restrict__ prims, int k, f3 o, f3 d, float tmin, float& tmax,
                                       float& b1o, float& b2o) {
-  float4 a = ldg4(prims + 3 * k), b = ldg4(prims + 3 * k + 1);
-  if ((TR & BDPT_TRAIT_TRIS) || __float_as_int(b.w) >= 0) {  // triangle: a = {v0, prim id}, b = {e1, material}, c = {e2, -}
-    float4 c = ldg4(prims + 3 * k + 2);
-    f3 e1 = mk3(b.x, b.y, b.z), e2 = mk3(c.x, c.y, c.z);
-    f3 s = o - mk3(a.x, a.y, a.z);
-    f3 s1 = cross(d, e2), s2 = cross(s, e1);
-    float inv = rcp_fast(dot(s1, e1));   // the winner is re-intersected in fp64 (finish_hit)
-    float t = dot(s2, e2) * inv, b1 = dot(s1, s) * inv, b2 = dot(s2, d) * inv;
+  const float4 a = ldg4(prims + 3 * k), c = ldg4(prims + 3 * k + 2);
+  if ((TR & BDPT_TRAIT_TRIS) || c.w == c.w) {
+    // triangle: rows of world -> (u, v, w); the ray meets w = 0 at t, and (u, v) of that point are the barycentrics
+    const float4 b = ldg4(prims + 3 * k + 1);
+    const float ow = fmaf(c.x, o.x, fmaf(c.y, o.y, fmaf(c.z, o.z, c.w)));
+    const float dw = fmaf(c.x, d.x, fmaf(c.y, d.y, c.z * d.z));
+    const float t = -ow * rcp_fast(dw);            // the winner is re-intersected in fp64 (finish_hit)
+    // (hit point first, then its two coordinates: the form O + t D per coordinate, and an early exit on t, were both slower)
+    const float px = fmaf(t, d.x, o.x), py = fmaf(t, d.y, o.y), pz = fmaf(t, d.z, o.z);
+    const float b1 = fmaf(a.x, px, fmaf(a.y, py, fmaf(a.z, pz, a.w)));
+    const float b2 = fmaf(b.x, px, fmaf(b.y, py, fmaf(b.z, pz, b.w)));
     if (t >= tmin && t <= tmax && b1 >= 0.f && b2 >= 0.f && b1 + b2 <= 1.f) {
       tmax = t; b1o = b1; b2o = b2;
       return true;
     }
     return false;
   }
-  // sphere: a = {centre, prim id}, b = {r, r^2, -, material | sign bit}
+  // sphere: a = {centre, r^2}
   f3 oc = o - mk3(a.x, a.y, a.z);
   float A = dot(d, d), hb = dot(oc, d);
   f3 l = oc - d * (hb / A);
-  float disc = A * (b.y - dot(l, l));
+  float disc = A * (a.w - dot(l, l));
   if (disc < 0.f) return false;
   float sd = sqrtf(disc), ia = 1.0f / A;
   float t1 = (-hb - sd) * ia, t2 = (-hb + sd) * ia, t = -1.f;
@@ -199,9 +203,9 @@ __device__ inline Hit traverse(const DScene& sc, f3 o, f3 d, float tmin, float t
 // surface and the EPS_F = 1e-5 self-intersection offsets meaningful.
 template <int TR = 0>
 __device__ inline void finish_hit(const DScene& sc, Hit& h, f3 o, f3 d, f3* n, int* prim_id, int* mat, f3* hit_p) {
-  float4 a = ldg4(sc.prims + 3 * h.leaf), b = ldg4(sc.prims + 3 * h.leaf + 1);
-  *prim_id = __float_as_int(a.w);
-  int mw = __float_as_int(b.w);
+  const float4 n1 = ldg4(sc.shading + 3 * h.leaf), n2 = ldg4(sc.shading + 3 * h.leaf + 1);
+  *prim_id = __float_as_int(n1.w);
+  int mw = __float_as_int(n2.w);
   *mat = mw & 0x7fffffff;
   const double* g = sc.prims64 + 10 * (size_t)h.leaf;
   const double ox = o.x, oy = o.y, oz = o.z, dx = d.x, dy = d.y, dz = d.z;
@@ -224,7 +228,7 @@ __device__ inline void finish_hit(const DScene& sc, Hit& h, f3 o, f3 d, f3* n, i
     } else {
       *hit_p = o + d * h.t;
     }
-    float4 n1 = ldg4(sc.shading + 3 * h.leaf), n2 = ldg4(sc.shading + 3 * h.leaf + 1), n3 = ldg4(sc.shading + 3 * h.leaf + 2);
+    const float4 n3 = ldg4(sc.shading + 3 * h.leaf + 2);
     float b0 = 1.f - h.b1 - h.b2;
     f3 nn = mk3(n1.x, n1.y, n1.z) * b0 + h.b1 * mk3(n2.x, n2.y, n2.z) + h.b2 * mk3(n3.x, n3.y, n3.z);
     *n = normalized(nn);
