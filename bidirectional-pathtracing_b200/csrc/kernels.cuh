@@ -752,6 +752,14 @@ __device__ inline unsigned warp_fetch_chunk(const Job& J, unsigned nchunks, bool
     const uint2 d = __ldg(J.chunks + c);
     wf.next = d.x;
     wf.end = d.x + d.y;
+    // the chunk's entries are handed out over the next rounds: request them into L2 (256 x 32 B of rays, 256 x 16 B of
+    // contributions; shadow kernel -1.8 %)
+    {
+      const char* r0 = (const char*)(J.q0 + 2 * (size_t)d.x); const unsigned nb0 = d.y * 32u;
+      for (unsigned off = (unsigned)lane * 128u; off < nb0; off += 32u * 128u) asm volatile("prefetch.global.L2 [%0];" :: "l"(r0 + off));
+      const char* r2 = (const char*)(J.q2 + (size_t)d.x); const unsigned nb2 = d.y * 16u;
+      for (unsigned off = (unsigned)lane * 128u; off < nb2; off += 32u * 128u) asm volatile("prefetch.global.L2 [%0];" :: "l"(r2 + off));
+    }
   }
   const unsigned my = wf.next + __popc(mask & ((1u << lane) - 1u));
   const bool got = want && my < wf.end;

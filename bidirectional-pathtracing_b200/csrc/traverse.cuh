@@ -79,6 +79,7 @@ struct Trav {
   float tmin;
   uint32_t oct;
   uint2 group;
+  uint2 tg;   // closest-hit only: a copy of stack[sp - 1], loaded one pop early (below)
   int sp;
   Hit hit;
 
@@ -106,7 +107,7 @@ struct Trav {
     group.y &= ~(1u << bit);
     uint32_t base = group.x;
     uint32_t imask_prev = group.y & 0xffu;
-    if (group.y > 0x00ffffffu) stack[sp++] = group;
+    if (group.y > 0x00ffffffu) { stack[sp++] = group; if (!ANY_HIT) tg = group; }
     uint32_t slot = (bit - 24u) ^ octinv;
     uint32_t rel = __popc(imask_prev & ((1u << slot) - 1u));
     const uint32_t ni = base + rel;
@@ -167,6 +168,8 @@ struct Trav {
 
     // ---- leaf primitives of this node that were hit
     uint32_t tris = hitmask & 0x00ffffffu;
+    // (prefetch.global.L1 of the records behind the first, or of the node the next step visits, made the kernels 3x /
+    // 10 % slower: the L1 prefetch path is not one to lean on here)
     while (tris) {
       int i = __ffs(tris) - 1;
       tris &= tris - 1u;
@@ -178,7 +181,15 @@ struct Trav {
     }
     if (group.y <= 0x00ffffffu) {
       if (sp == 0) return true;
-      group = stack[--sp];
+      if (!ANY_HIT) {
+        // the popped entry comes from a register; the one below it is requested now and not needed before the next pop
+        // or push — the local-memory latency hides behind the node visits in between (walk -1.8 %; the any-hit kernel
+        // has no registers to spare for it: +5 %)
+        group = tg; --sp;
+        if (sp > 0) tg = stack[sp - 1];
+      } else {
+        group = stack[--sp];
+      }
     }
     return false;
   }
