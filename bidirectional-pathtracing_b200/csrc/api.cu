@@ -252,6 +252,14 @@ void fill_job(BdptContext* ctx, const BdptRenderParams* p, Job* J) {
   J->single_x = -1; J->single_y = -1;
 }
 
+// k_walk_pt's thresholds: lanes that must want shading before the warp shades / idle lanes it tolerates before it fetches
+#ifndef BDPT_WALK_ST
+#define BDPT_WALK_ST 14
+#endif
+#ifndef BDPT_WALK_FT
+#define BDPT_WALK_FT 6
+#endif
+
 // Launches k_connect in the build the scene's traits allow (the trait never depends on the tuning knob).
 template <bool TRACE, int TR>
 void launch_connect(BdptContext* ctx, const Job& J, unsigned grid, int minb) {
@@ -281,13 +289,13 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
     const size_t shm = (size_t)J.ntop * 80;
     if (ctx->variant == 1 && !lens) k_walk_pt<16, 8, 4><<<g, threads, shm, ctx->stream>>>(J);
     else switch (wtr) {
-      case 1: k_walk_pt<14, 6, 6, 1><<<g, threads, shm, ctx->stream>>>(J); break;
-      case 2: k_walk_pt<14, 6, 6, 2><<<g, threads, shm, ctx->stream>>>(J); break;
-      case 3: k_walk_pt<14, 6, 6, 3><<<g, threads, shm, ctx->stream>>>(J); break;
-      case 4: k_walk_pt<14, 6, 6, 4><<<g, threads, shm, ctx->stream>>>(J); break;
-      case 5: k_walk_pt<14, 6, 6, 5><<<g, threads, shm, ctx->stream>>>(J); break;
-      case BDPT_TRAIT_LENS: k_walk_pt<14, 6, 6, BDPT_TRAIT_LENS><<<g, threads, shm, ctx->stream>>>(J); break;
-      default: k_walk_pt<14, 6, 6, 0><<<g, threads, shm, ctx->stream>>>(J); break;
+      case 1: k_walk_pt<BDPT_WALK_ST, BDPT_WALK_FT, 6, 1><<<g, threads, shm, ctx->stream>>>(J); break;
+      case 2: k_walk_pt<BDPT_WALK_ST, BDPT_WALK_FT, 6, 2><<<g, threads, shm, ctx->stream>>>(J); break;
+      case 3: k_walk_pt<BDPT_WALK_ST, BDPT_WALK_FT, 6, 3><<<g, threads, shm, ctx->stream>>>(J); break;
+      case 4: k_walk_pt<BDPT_WALK_ST, BDPT_WALK_FT, 6, 4><<<g, threads, shm, ctx->stream>>>(J); break;
+      case 5: k_walk_pt<BDPT_WALK_ST, BDPT_WALK_FT, 6, 5><<<g, threads, shm, ctx->stream>>>(J); break;
+      case BDPT_TRAIT_LENS: k_walk_pt<BDPT_WALK_ST, BDPT_WALK_FT, 6, BDPT_TRAIT_LENS><<<g, threads, shm, ctx->stream>>>(J); break;
+      default: k_walk_pt<BDPT_WALK_ST, BDPT_WALK_FT, 6, 0><<<g, threads, shm, ctx->stream>>>(J); break;
     }
   } else {
     const unsigned g = (unsigned)((2 * J.B + threads - 1) / threads);
