@@ -99,8 +99,10 @@ struct Trav {
   // scalar state stays in registers)
   // `top` (optional): the first `ntop` nodes of the tree — its upper levels, the builder emits nodes breadth
   // first — staged in shared memory by the calling kernel.
-  template <bool ANY_HIT, int TR = 0>
-  __device__ inline bool step(const DScene& sc, uint2* stack, const uint4* top = nullptr, const uint32_t ntop = 0) {
+  // One node visit: pop the nearest pending internal child of the current group, test its 8 children; the hit internal
+  // children become the current group; the hit leaf primitives are returned as a bit set (bit i = primitive *pbase + i).
+  template <bool ANY_HIT>
+  __device__ inline uint32_t node_visit(const DScene& sc, uint2* stack, const uint4* top, const uint32_t ntop, int* pbase) {
     const uint32_t octinv = oct ^ 7u;
     // ---- pop the nearest internal child of the current group
     uint32_t bit = 31u - (uint32_t)__clz(group.y);
@@ -166,19 +168,28 @@ struct Trav {
     }
     group = make_uint2(q1.x, (hitmask & 0xff000000u) | imask);
 
-    // ---- leaf primitives of this node that were hit
-    uint32_t tris = hitmask & 0x00ffffffu;
-    // (prefetch.global.L1 of the records behind the first, or of the node the next step visits, made the kernels 3x /
-    // 10 % slower: the L1 prefetch path is not one to lean on here)
+    *pbase = (int)q1.y;
+    return hitmask & 0x00ffffffu;
+  }
+
+  // Primitive tests of a leaf set; true = an any-hit ray found its hit.
+  template <bool ANY_HIT, int TR>
+  __device__ inline bool leaf_tests(const DScene& sc, uint32_t tris, int pbase) {
     while (tris) {
       int i = __ffs(tris) - 1;
       tris &= tris - 1u;
-      int k = (int)q1.y + i;
+      int k = pbase + i;
       if (intersect_prim<TR>(sc.prims, k, o, d, tmin, hit.t, hit.b1, hit.b2)) {
         hit.leaf = k;
         if (ANY_HIT) return true;
       }
     }
+    return false;
+  }
+
+  // The current group has no pending child left: take the next one from the stack.  True = the traversal is over.
+  template <bool ANY_HIT>
+  __device__ inline bool next_group(uint2* stack) {
     if (group.y <= 0x00ffffffu) {
       if (sp == 0) return true;
       if (!ANY_HIT) {
@@ -193,6 +204,15 @@ struct Trav {
     }
     return false;
   }
+
+  template <bool ANY_HIT, int TR = 0>
+  __device__ inline bool step(const DScene& sc, uint2* stack, const uint4* top = nullptr, const uint32_t ntop = 0) {
+    int pbase;
+    const uint32_t tris = node_visit<ANY_HIT>(sc, stack, top, ntop, &pbase);
+    if (leaf_tests<ANY_HIT, TR>(sc, tris, pbase)) return true;
+    return next_group<ANY_HIT>(stack);
+  }
+
 };
 
 template <bool ANY_HIT, int TR = 0>
