@@ -656,7 +656,15 @@ def test_large_mesh_device_tree_renders_like_the_host_tree(api, monkeypatch):
     monkeypatch.setenv("BDPT_BVH", "host")
     B = api.Renderer(0, ns_aa=4, max_ray_depth=5, seed=3); B.set_scene(sc); B.set_frame_size(W, H); B.render()
     assert relmse(A.framebuffer(0), B.framebuffer(0)) <= 1e-6
-    assert A.stats()["ms_bvh_build"] < B.stats()["ms_bvh_build"]
+    # ingest time, steady state (a context's first upload also pays its cudaMallocs, which now and then take 0.1-0.7 s)
+    tb = []
+    for _ in range(2):
+        B.set_scene(sc); tb.append(B.stats()["ms_bvh_build"])
+    monkeypatch.delenv("BDPT_BVH")
+    ta = []
+    for _ in range(3):
+        A.set_scene(sc); ta.append(A.stats()["ms_bvh_build"])
+    assert min(ta) < min(tb), (ta, tb)
 
 
 def test_no_mis_switch_matches_oracle(api, O):
