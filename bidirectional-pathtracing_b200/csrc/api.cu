@@ -32,7 +32,9 @@ struct BdptContext {
   bool have_scene = false;
   BdptCamera cam_base{};
   DScene sc{};
-  uint4* d_nodes = nullptr;
+  uint4* d_nodes = nullptr;        // the builders' output: 80 bytes a node (what bdpt_device_bvh exports)
+  uint4* d_nodes_wide = nullptr;   // the same nodes at a stride of 96 bytes: what the kernels traverse (DScene::nodes)
+  size_t cap_nodes_wide = 0;
   float4 *d_prims = nullptr, *d_shading = nullptr, *d_mats = nullptr, *d_lights = nullptr;
   double* d_prims64 = nullptr;
   size_t cap_scene[6] = {0, 0, 0, 0, 0, 0};
@@ -385,7 +387,7 @@ int build_scene_on_device(BdptContext* ctx, const BdptPrim* prims, uint32_t n_pr
   const size_t n2 = 2 * (size_t)N;
   cudaStream_t st = ctx->stream;
   // scene arrays (grow-only)
-  if (ensure_dev((void**)&ctx->d_nodes, &ctx->cap_scene[0], (size_t)N * 80) || ensure_dev((void**)&ctx->d_prims, &ctx->cap_scene[1], 3 * (size_t)N * sizeof(float4)) ||
+  if (ensure_dev((void**)&ctx->d_nodes, &ctx->cap_scene[0], (size_t)N * 80) || ensure_dev((void**)&ctx->d_prims, &ctx->cap_scene[1], BDPT_PRIM_Q * (size_t)N * sizeof(float4)) ||
       ensure_dev((void**)&ctx->d_shading, &ctx->cap_scene[2], 3 * (size_t)N * sizeof(float4)) || ensure_dev((void**)&ctx->d_prims64, &ctx->cap_scene[5], 10 * (size_t)N * sizeof(double)))
     return fail(ctx, BDPT_ERR_CUDA, "cudaMalloc (scene arrays)");
   // workspace
@@ -526,7 +528,7 @@ void bdpt_destroy(BdptContext* ctx) {
   bdpt_comm_destroy(ctx);
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  dfree(ctx->d_nodes); dfree(ctx->d_prims); dfree(ctx->d_shading); dfree(ctx->d_mats); dfree(ctx->d_lights); dfree(ctx->d_prims64);
+  dfree(ctx->d_nodes); dfree(ctx->d_nodes_wide); dfree(ctx->d_prims); dfree(ctx->d_shading); dfree(ctx->d_mats); dfree(ctx->d_lights); dfree(ctx->d_prims64);
   dfree(ctx->acc); dfree(ctx->resolve_tmp); dfree(ctx->rgba_tmp);
   dfree(ctx->slab); dfree(ctx->counters); ctx->qctr = nullptr; ctx->d_stats = nullptr;
   if (ctx->h_qctr) cudaFreeHost(ctx->h_qctr);
@@ -642,10 +644,10 @@ int bdpt_upload_scene(BdptContext* ctx, const BdptCamera* camera, const BdptMate
     }
     if (bvh.max_depth >= BDPT_STACK) return fail(ctx, BDPT_ERR_SCENE, "BVH deeper than the traversal stack");
     // leaf-ordered primitive + shading records
-    std::vector<float4> hp(3 * (size_t)std::max<uint32_t>(n_prims, 1)), hs(3 * (size_t)std::max<uint32_t>(n_prims, 1));
+    std::vector<float4> hp(BDPT_PRIM_Q * (size_t)std::max<uint32_t>(n_prims, 1)), hs(3 * (size_t)std::max<uint32_t>(n_prims, 1));
     std::vector<double> h64(10 * (size_t)std::max<uint32_t>(n_prims, 1), 0.0);
     for (size_t k = 0; k < bvh.prim_order.size(); k++)
-      make_leaf_record(prims[bvh.prim_order[k]], bvh.prim_order[k], hp.data() + 3 * k, hs.data() + 3 * k, h64.data() + 10 * k);
+      make_leaf_record(prims[bvh.prim_order[k]], bvh.prim_order[k], hp.data() + BDPT_PRIM_Q * k, hs.data() + 3 * k, h64.data() + 10 * k);
     CK(ensure((void**)&ctx->d_nodes, &ctx->cap_scene[0], bvh.nodes.size() * sizeof(uint32_t)));
     CK(ensure((void**)&ctx->d_prims, &ctx->cap_scene[1], hp.size() * sizeof(float4)));
     CK(ensure((void**)&ctx->d_shading, &ctx->cap_scene[2], hs.size() * sizeof(float4)));
@@ -658,11 +660,15 @@ int bdpt_upload_scene(BdptContext* ctx, const BdptCamera* camera, const BdptMate
     ctx->d_prim_order = nullptr;
     n_nodes = (uint32_t)(bvh.nodes.size() / 20); depth = bvh.max_depth;
   }
+  // the traversal's copy of the nodes: 96 bytes apart, so that a node is three aligned 32-byte loads
+  if (ensure_dev((void**)&ctx->d_nodes_wide, &ctx->cap_nodes_wide, (size_t)std::max<uint32_t>(n_nodes, 1) * BDPT_NODE_Q * sizeof(uint4)))
+    return fail(ctx, BDPT_ERR_CUDA, "cudaMalloc (nodes)");
+  if (n_nodes) CK(cudaMemcpy2DAsync(ctx->d_nodes_wide, BDPT_NODE_Q * sizeof(uint4), ctx->d_nodes, 80, 80, n_nodes, cudaMemcpyDeviceToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   // (historical name: the whole scene ingest — build, records, copies — since the build moved to the device)
   ctx->ms_bvh_build = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 
-  ctx->sc.nodes = ctx->d_nodes; ctx->sc.prims = ctx->d_prims; ctx->sc.shading = ctx->d_shading; ctx->sc.prims64 = ctx->d_prims64;
+  ctx->sc.nodes = ctx->d_nodes_wide; ctx->sc.prims = ctx->d_prims; ctx->sc.shading = ctx->d_shading; ctx->sc.prims64 = ctx->d_prims64;
   ctx->sc.materials = ctx->d_mats; ctx->sc.lights = ctx->d_lights;
   ctx->sc.n_lights = (int)n_lights; ctx->sc.n_materials = (int)n_materials;
   ctx->sc.env_light = env_light;

@@ -245,11 +245,11 @@ __global__ void k_bvh_emit_level(DevTree T, const uint8_t* split, const uint8_t*
 }
 
 // ---- leaf-ordered records the traversal and shading read (one definition for the device build and the host one)
-//   prims   3 x float4 per leaf slot.  Triangle: the three rows of the affine map world -> (u, v, w) with
+//   prims   BDPT_PRIM_Q float4 per leaf slot, in the order {w row, u row, v row}.  Triangle: the three rows of the affine map world -> (u, v, w) with
 //           p = v0 + u e1 + v e2 + w n, n = e1 x e2 (the "unit triangle" form of Woop et al.; computed in fp64): a ray test
 //           is 5 three-term dot products and one reciprocal instead of Moller-Trumbore's two cross products and four.
 //           A degenerate triangle gets zero rows (never hit, as in the reference: triangle.cpp:57-95 divides by 0 and
-//           every comparison with the NaN fails).  Sphere: {centre, r^2}, -, {0, 0, 0, NaN} (the NaN is the type tag).
+//           every comparison with the NaN fails).  Sphere: {0, 0, 0, NaN} (the NaN is the type tag), {centre, r^2}, -, -.
 //   shading 3 x float4: the vertex normals; .w of the first two: primitive id in build_accel order, material
 //           (| sign bit for a sphere)
 //   prims64 10 doubles: the fp64 geometry finish_hit re-intersects the winner with
@@ -272,16 +272,17 @@ __host__ __device__ inline void make_leaf_record(const BdptPrim& p, uint32_t id,
       R[2][0] = n[0] * inv; R[2][1] = n[1] * inv; R[2][2] = n[2] * inv;
       for (int r = 0; r < 3; r++) R[r][3] = -(R[r][0] * d[0] + R[r][1] * d[1] + R[r][2] * d[2]);
     }
-    for (int r = 0; r < 3; r++) hp[r] = make_float4((float)R[r][0], (float)R[r][1], (float)R[r][2], (float)R[r][3]);
+    for (int r = 0; r < 3; r++) hp[(r + 1) % 3] = make_float4((float)R[r][0], (float)R[r][1], (float)R[r][2], (float)R[r][3]);   // {w, u, v}
+    if (BDPT_PRIM_Q > 3) hp[BDPT_PRIM_Q - 1] = make_float4(0.f, 0.f, 0.f, 0.f);
     hs[0] = make_float4((float)d[9], (float)d[10], (float)d[11], idb.f);
     hs[1] = make_float4((float)d[12], (float)d[13], (float)d[14], matb.f);
     hs[2] = make_float4((float)d[15], (float)d[16], (float)d[17], 0.f);
   } else {
     matb.i = p.material | (int)0x80000000;
     union { unsigned u; float f; } nan; nan.u = 0x7fc00000u;
-    hp[0] = make_float4((float)d[0], (float)d[1], (float)d[2], (float)(d[3] * d[3]));
-    hp[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-    hp[2] = make_float4(0.f, 0.f, 0.f, nan.f);
+    hp[0] = make_float4(0.f, 0.f, 0.f, nan.f);
+    hp[1] = make_float4((float)d[0], (float)d[1], (float)d[2], (float)(d[3] * d[3]));
+    hp[2] = hp[BDPT_PRIM_Q - 1] = make_float4(0.f, 0.f, 0.f, 0.f);
     hs[0] = make_float4(0.f, 0.f, 0.f, idb.f);
     hs[1] = make_float4(0.f, 0.f, 0.f, matb.f);
     hs[2] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -292,7 +293,7 @@ __global__ void k_bvh_records(const BdptPrim* prims, const uint32_t* prim_order,
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const uint32_t id = prim_order[k];
-  make_leaf_record(prims[id], id, hp + 3 * (size_t)k, hs + 3 * (size_t)k, h64 + 10 * (size_t)k);
+  make_leaf_record(prims[id], id, hp + BDPT_PRIM_Q * (size_t)k, hs + 3 * (size_t)k, h64 + 10 * (size_t)k);
 }
 
 }  // namespace bdpt

@@ -104,9 +104,17 @@ struct alignas(16) Node8 {  // 80 bytes, see bvh8.h
 // every build it cost the walk kernel 2 %).
 #define BDPT_TRAIT_LENS 8
 
+#ifndef BDPT_NODE_Q
+#define BDPT_NODE_Q 6   // uint4 per node in the traversal array (the builders emit 5; the sixth is padding): shadow kernel -2.6 %
+#endif
+#ifndef BDPT_PRIM_Q
+#define BDPT_PRIM_Q 3   // float4 per leaf primitive record (4 = padded to 64 bytes, first two rows in one 32-byte load: measured
+                        // slower, walk +2 %, shadow +3.9 % — the records' footprint grows by a third)
+#endif
+
 struct DScene {
-  const uint4* nodes;       // Node8 as 5 x uint4
-  const float4* prims;      // leaf-ordered primitive records, 3 x float4 each (layouts: bvh_gpu.cuh, make_leaf_record)
+  const uint4* nodes;       // Node8 (5 x uint4) at a stride of BDPT_NODE_Q uint4: 96 bytes, three 32-byte loads
+  const float4* prims;      // leaf-ordered primitive records, BDPT_PRIM_Q float4 each (layouts: bvh_gpu.cuh, make_leaf_record)
   const float4* shading;    // leaf-ordered shading normals n1,n2,n3, 3 x float4 each; .w: primitive id, material, -
   const double* prims64;    // leaf-ordered fp64 geometry, 10 doubles each: triangle p1 p2 p3 (+pad) / sphere c, r
   const float4* materials;  // DMaterial as 5 x float4
@@ -148,6 +156,16 @@ __host__ __device__ inline uint32_t fast_div(uint32_t n, const FastDiv& f) {
 // 1/x by the SFU alone (MUFU.RCP, <= 1 ulp on normal inputs; denormals flush): __fdividef(1, x) adds a range fix-up
 __device__ inline float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
+// 32-byte read-only loads (LDG.E.256.CONSTANT, sm_100): one L1 wavefront per lane where two 16-byte loads take two — the
+// traversal kernels run the L1 data pipe at 62-77 % of its wavefront peak (profiles/README.md, r02d)
+__device__ inline void ld256nc(const uint4* p, uint4* a, uint4* b) {
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a->x), "=r"(a->y), "=r"(a->z), "=r"(a->w), "=r"(b->x), "=r"(b->y), "=r"(b->z), "=r"(b->w) : "l"(p));
+}
+__device__ inline void ld256nc(const float4* p, float4* a, float4* b) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a->x), "=f"(a->y), "=f"(a->z), "=f"(a->w), "=f"(b->x), "=f"(b->y), "=f"(b->z), "=f"(b->w) : "l"(p));
+}
 __device__ inline float4 ldg4(const float4* p) { return __ldg(p); }
 __device__ inline uint4 ldg4(const uint4* p) { return __ldg(p); }
 

@@ -769,7 +769,7 @@ __device__ inline unsigned warp_fetch_chunk(const Job& J, unsigned nchunks, bool
 
 // Copies the first `ntop` BVH nodes (the upper levels: nodes are stored breadth first) into shared memory.
 __device__ inline void stage_top_nodes(const Job& J, uint4* top) {
-  for (int i = threadIdx.x; i < J.ntop * 5; i += blockDim.x) top[i] = J.sc.nodes[i];
+  for (int i = threadIdx.x; i < J.ntop * 5; i += blockDim.x) top[i] = J.sc.nodes[(i / 5) * BDPT_NODE_Q + i % 5];
   __syncthreads();
 }
 

@@ -39,10 +39,15 @@ __device__ inline float qbyte(uint32_t w, int k, uint32_t bias_bits) {   // bias
 template <int TR = 0>
 __device__ inline bool intersect_prim(const float4* __restrict__ prims, int k, f3 o, f3 d, float tmin, float& tmax,
                                       float& b1o, float& b2o) {
-  const float4 a = ldg4(prims + 3 * k), c = ldg4(prims + 3 * k + 2);
+  float4 c, a;
+#if BDPT_PRIM_Q == 4
+  ld256nc(prims + BDPT_PRIM_Q * k, &c, &a);
+#else
+  c = ldg4(prims + BDPT_PRIM_Q * k); a = ldg4(prims + BDPT_PRIM_Q * k + 1);
+#endif
   if ((TR & BDPT_TRAIT_TRIS) || c.w == c.w) {
     // triangle: rows of world -> (u, v, w); the ray meets w = 0 at t, and (u, v) of that point are the barycentrics
-    const float4 b = ldg4(prims + 3 * k + 1);
+    const float4 b = ldg4(prims + BDPT_PRIM_Q * k + 2);
     const float ow = fmaf(c.x, o.x, fmaf(c.y, o.y, fmaf(c.z, o.z, c.w)));
     const float dw = fmaf(c.x, d.x, fmaf(c.y, d.y, c.z * d.z));
     const float t = -ow * rcp_fast(dw);            // the winner is re-intersected in fp64 (finish_hit)
@@ -118,8 +123,12 @@ struct Trav {
       const uint4* np = top + (size_t)ni * 5;
       q0 = np[0]; q1 = np[1]; q2 = np[2]; q3 = np[3]; q4 = np[4];
     } else {
-      const uint4* np = sc.nodes + (size_t)ni * 5;
+      const uint4* np = sc.nodes + (size_t)ni * BDPT_NODE_Q;
+#if BDPT_NODE_Q == 6
+      ld256nc(np, &q0, &q1); ld256nc(np + 2, &q2, &q3); q4 = ldg4(np + 4);
+#else
       q0 = ldg4(np); q1 = ldg4(np + 1); q2 = ldg4(np + 2); q3 = ldg4(np + 3); q4 = ldg4(np + 4);
+#endif
     }
 
     f3 adj, org;   // plane q of an axis is hit at t = (2^15 + q) * adj + org
