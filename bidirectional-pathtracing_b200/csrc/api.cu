@@ -44,8 +44,13 @@ struct BdptContext {
   // device build (bvh_gpu.cuh): workspace (grow-only), pinned counters, the leaf order it produced
   char* bvh_ws = nullptr; size_t bvh_ws_bytes = 0;
   unsigned int* h_bvh = nullptr;
-  uint32_t* d_prim_order = nullptr;     // points into bvh_ws
-  int bvh_on_device = 1;                // BDPT_BVH=host builds on the host instead (bvh8.cpp: the checker)
+  uint32_t* d_prim_order = nullptr;     // device build: points into bvh_ws; null after a host build, whose order is kept in
+  std::vector<uint32_t> h_prim_order;   // ... here (what bdpt_device_bvh exports)
+  // where the BVH is built: 2 (default) = on the device unless the scene has at most BDPT_SMALL_SCENE primitives, for which
+  // the host restatement of the same PLOC build (same tree, node for node) is quicker than ~50 tiny launches
+  // (252 primitives: 0.26 against 1.05 ms); 1 = always on the device (BDPT_BVH=device); 0 = binned SAH on the host
+  // (BDPT_BVH=host, bvh8.cpp: the checker)
+  int bvh_on_device = 2;
   uint32_t bvh_rounds = 0;              // PLOC rounds of the last device build
 
   // frame
@@ -261,6 +266,8 @@ void fill_job(BdptContext* ctx, const BdptRenderParams* p, Job* J) {
 #ifndef BDPT_WALK_FT
 #define BDPT_WALK_FT 6
 #endif
+
+#define BDPT_SMALL_SCENE 1024u   // primitives up to which the host builds the (same) PLOC tree; crossover measured near 1,500
 
 // Launches k_connect in the build the scene's traits allow (the trait never depends on the tuning knob).
 template <bool TRACE, int TR>
@@ -517,7 +524,7 @@ int bdpt_create(int device, BdptContext** out) {
   if (const char* e = getenv("BDPT_VARIANT")) ctx->variant = atoi(e);
   if (const char* e = getenv("BDPT_WALK_CTAS")) ctx->walk_ctas = std::max(1, atoi(e));
   if (const char* e = getenv("BDPT_SHADOW_CTAS")) ctx->shadow_ctas = std::max(1, atoi(e));
-  if (const char* e = getenv("BDPT_BVH")) ctx->bvh_on_device = strcmp(e, "host") != 0;
+  if (const char* e = getenv("BDPT_BVH")) ctx->bvh_on_device = !strcmp(e, "host") ? 0 : !strcmp(e, "device") ? 1 : 2;
   if (cudaMallocHost(&ctx->h_bvh, 16 * sizeof(unsigned int)) != cudaSuccess) { g_create_error = "cudaMallocHost failed"; cudaStreamDestroy(ctx->stream); delete ctx; return BDPT_ERR_CUDA; }
   *out = ctx;
   return BDPT_OK;
@@ -628,19 +635,21 @@ int bdpt_upload_scene(BdptContext* ctx, const BdptCamera* camera, const BdptMate
   CK(cudaMemcpyAsync(ctx->d_lights, hl.data(), hl.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
 
   uint32_t n_nodes = 0, depth = 0;
-  if (ctx->bvh_on_device && n_prims >= 1) {
+  const bool small_scene = ctx->bvh_on_device == 2 && n_prims <= BDPT_SMALL_SCENE;
+  if (ctx->bvh_on_device && !small_scene && n_prims >= 1) {
     // the raw primitives go up as they are; bounds, Morton order, PLOC, the 8-wide collapse and the leaf-ordered
     // records are all made on the device (bvh_gpu.cuh) — what BVHAccel::construct_bvh does on one host thread
     int rc = build_scene_on_device(ctx, prims, n_prims, &n_nodes, &depth);
     if (rc) return rc;
   } else {
-    // BDPT_BVH=host (and the empty scene): binned-SAH build on the host (bvh8.cpp), kept as the checker
+    // BDPT_BVH=host (and the empty scene): binned-SAH build on the host (bvh8.cpp), kept as the checker; small scenes:
+    // the PLOC build, on the host
     std::vector<BuildPrim> bp;
     make_build_prims(prims, n_prims, &bp);
     Bvh8 bvh;
     {
       const char* algo = getenv("BDPT_BVH_HOST_ALGO");
-      if (algo && !strcmp(algo, "ploc")) build_bvh8_ploc(bp, &bvh); else build_bvh8(bp, &bvh);
+      if (small_scene || (algo && !strcmp(algo, "ploc"))) build_bvh8_ploc(bp, &bvh); else build_bvh8(bp, &bvh);
     }
     if (bvh.max_depth >= BDPT_STACK) return fail(ctx, BDPT_ERR_SCENE, "BVH deeper than the traversal stack");
     // leaf-ordered primitive + shading records
@@ -657,7 +666,7 @@ int bdpt_upload_scene(BdptContext* ctx, const BdptCamera* camera, const BdptMate
     CK(cudaMemcpyAsync(ctx->d_prims, hp.data(), hp.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_shading, hs.data(), hs.size() * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));   // the staging vectors go out of scope
-    ctx->d_prim_order = nullptr;
+    ctx->d_prim_order = nullptr; ctx->h_prim_order = bvh.prim_order;
     n_nodes = (uint32_t)(bvh.nodes.size() / 20); depth = bvh.max_depth;
   }
   // the traversal's copy of the nodes: 96 bytes apart, so that a node is three aligned 32-byte loads
@@ -919,8 +928,8 @@ int bdpt_device_bvh(BdptContext* ctx, uint32_t* nodes_out, uint32_t nodes_cap, u
     CK(cudaMemcpyAsync(nodes_out, ctx->d_nodes, (size_t)ctx->bvh_nodes * 80, cudaMemcpyDeviceToHost, ctx->stream));
   }
   if (prim_order_out) {
-    if (!ctx->d_prim_order) return fail(ctx, BDPT_ERR_ARG, "the scene was built on the host (BDPT_BVH=host): use bdpt_host_build_bvh");
-    CK(cudaMemcpyAsync(prim_order_out, ctx->d_prim_order, (size_t)ctx->sc.n_prims * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->d_prim_order) CK(cudaMemcpyAsync(prim_order_out, ctx->d_prim_order, (size_t)ctx->sc.n_prims * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    else memcpy(prim_order_out, ctx->h_prim_order.data(), ctx->h_prim_order.size() * 4);   // built on the host (small scene, or BDPT_BVH=host)
   }
   CK(cudaStreamSynchronize(ctx->stream));
   return BDPT_OK;

@@ -153,9 +153,11 @@ int bdpt_comm_destroy(BdptContext* ctx);
  * nodes_out = NULL to query n_nodes first.  Stands where BVHAccel::construct_bvh does (bvh.cpp:51-129). */
 int bdpt_host_build_bvh(const BdptPrim* prims, uint32_t n_prims, uint32_t* nodes_out, uint32_t nodes_cap,
                         uint32_t* n_nodes, uint32_t* prim_order_out, uint32_t* max_depth);
-/* The tree bdpt_upload_scene built ON THE DEVICE for the current scene (Morton order + PLOC + the same 8-wide collapse,
- * bidirectional-pathtracing_b200/csrc/bvh_gpu.cuh), copied back for inspection: same layout as above; *rounds = PLOC
- * rounds it took.  Pass nodes_out = NULL to query n_nodes first. */
+/* The tree bdpt_upload_scene built for the current scene — on the device (Morton order + PLOC + the same 8-wide collapse,
+ * bidirectional-pathtracing_b200/csrc/bvh_gpu.cuh), or, for scenes of at most 1,024 primitives, by the host restatement
+ * of that build (the same tree; BDPT_BVH=device forces the device) — copied back for inspection: same layout as above;
+ * *rounds = PLOC rounds the device build took (0 = the tree came from the host).  Pass nodes_out = NULL to query
+ * n_nodes first. */
 int bdpt_device_bvh(BdptContext* ctx, uint32_t* nodes_out, uint32_t nodes_cap, uint32_t* n_nodes, uint32_t* prim_order_out,
                     uint32_t* max_depth, uint32_t* rounds);
 /* rays: n x {o[3], d[3], tmin, tmax} fp64 -> hits: n x {prim id (-1 miss), t, n[3], material} fp64.

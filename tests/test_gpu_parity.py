@@ -76,6 +76,7 @@ def test_device_built_bvh_is_sound_and_matches_the_host_restatement(api, name, m
     restatement (bvh8.cpp, build_bvh8_ploc) up to the order in which nodes of one level were numbered."""
     from test_host import bvh_cost, check_bvh_sound
     sc = load_scene(name)
+    monkeypatch.setenv("BDPT_BVH", "device")   # (by default scenes of <= 1024 primitives get this same tree from the host)
     R = make_renderer(api, name, 64, 48)
     nodes, order, depth, rounds = R.device_bvh()
     check_bvh_sound(sc, nodes, order, depth)
