@@ -22,6 +22,24 @@ namespace {
 thread_local std::string g_create_error = "";
 }
 
+// ---- build-time tuning of the persistent kernels (A/B: scripts/gpu_ab_lib.sh)
+// k_walk_pt's thresholds: lanes that must want shading before the warp shades / idle lanes it tolerates before it fetches
+#ifndef BDPT_WALK_ST
+#define BDPT_WALK_ST 14
+#endif
+#ifndef BDPT_WALK_FT
+#define BDPT_WALK_FT 6
+#endif
+#ifndef BDPT_WALK_MINB
+#define BDPT_WALK_MINB 6   // resident CTAs/SM k_walk_pt is compiled for (80 registers)
+#endif
+
+#ifndef BDPT_SHADOW_MINB
+#define BDPT_SHADOW_MINB 9    // resident CTAs/SM the triangle build of k_shadow_pt is compiled for: 56 registers, nothing spilled
+                              // (10: 48 registers, 36 B of spills in the hot loop, +3.8 %; 8: +0.2 %; 11: +15 %)
+#endif
+#define BDPT_SMALL_SCENE 1024u   // primitives up to which the host builds the (same) PLOC tree; crossover measured near 1,500
+
 struct BdptContext {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -101,7 +119,7 @@ struct BdptContext {
   // with a tail of long paths; at 2^24 samples per batch that tail is ~1 % of the step (2^22: ~4 %), and 48 of the
   // 180 GB are there to be used.  Storage is only ever allocated for the samples a render actually has.
   int batch_log2 = 24, batch_gib = 48;
-  int walk_ctas = 6, shadow_ctas = 0;  // resident CTAs per SM of the persistent kernels (shadow: 0 = the build's own, 10 or 8)
+  int walk_ctas = BDPT_WALK_MINB, shadow_ctas = 0;  // resident CTAs per SM of the persistent kernels (shadow: 0 = the build's own, 9 or 8)
   // multi-GPU (comm.inc): an ncclComm_t, bound at run time
   void* comm = nullptr; int comm_ranks = 0, comm_rank = 0;
 };
@@ -259,16 +277,6 @@ void fill_job(BdptContext* ctx, const BdptRenderParams* p, Job* J) {
   J->single_x = -1; J->single_y = -1;
 }
 
-// k_walk_pt's thresholds: lanes that must want shading before the warp shades / idle lanes it tolerates before it fetches
-#ifndef BDPT_WALK_ST
-#define BDPT_WALK_ST 14
-#endif
-#ifndef BDPT_WALK_FT
-#define BDPT_WALK_FT 6
-#endif
-
-#define BDPT_SMALL_SCENE 1024u   // primitives up to which the host builds the (same) PLOC tree; crossover measured near 1,500
-
 // Launches k_connect in the build the scene's traits allow (the trait never depends on the tuning knob).
 template <bool TRACE, int TR>
 void launch_connect(BdptContext* ctx, const Job& J, unsigned grid, int minb) {
@@ -298,13 +306,13 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
     const size_t shm = (size_t)J.ntop * 80;
     if (ctx->variant == 1 && !lens) k_walk_pt<16, 8, 4><<<g, threads, shm, ctx->stream>>>(J);
     else switch (wtr) {
-      case 1: k_walk_pt<BDPT_WALK_ST, BDPT_WALK_FT, 6, 1><<<g, threads, shm, ctx->stream>>>(J); break;
-      case 2: k_walk_pt<BDPT_WALK_ST, BDPT_WALK_FT, 6, 2><<<g, threads, shm, ctx->stream>>>(J); break;
-      case 3: k_walk_pt<BDPT_WALK_ST, BDPT_WALK_FT, 6, 3><<<g, threads, shm, ctx->stream>>>(J); break;
-      case 4: k_walk_pt<BDPT_WALK_ST, BDPT_WALK_FT, 6, 4><<<g, threads, shm, ctx->stream>>>(J); break;
-      case 5: k_walk_pt<BDPT_WALK_ST, BDPT_WALK_FT, 6, 5><<<g, threads, shm, ctx->stream>>>(J); break;
-      case BDPT_TRAIT_LENS: k_walk_pt<BDPT_WALK_ST, BDPT_WALK_FT, 6, BDPT_TRAIT_LENS><<<g, threads, shm, ctx->stream>>>(J); break;
-      default: k_walk_pt<BDPT_WALK_ST, BDPT_WALK_FT, 6, 0><<<g, threads, shm, ctx->stream>>>(J); break;
+      case 1: k_walk_pt<BDPT_WALK_ST, BDPT_WALK_FT, BDPT_WALK_MINB, 1><<<g, threads, shm, ctx->stream>>>(J); break;
+      case 2: k_walk_pt<BDPT_WALK_ST, BDPT_WALK_FT, BDPT_WALK_MINB, 2><<<g, threads, shm, ctx->stream>>>(J); break;
+      case 3: k_walk_pt<BDPT_WALK_ST, BDPT_WALK_FT, BDPT_WALK_MINB, 3><<<g, threads, shm, ctx->stream>>>(J); break;
+      case 4: k_walk_pt<BDPT_WALK_ST, BDPT_WALK_FT, BDPT_WALK_MINB, 4><<<g, threads, shm, ctx->stream>>>(J); break;
+      case 5: k_walk_pt<BDPT_WALK_ST, BDPT_WALK_FT, BDPT_WALK_MINB, 5><<<g, threads, shm, ctx->stream>>>(J); break;
+      case BDPT_TRAIT_LENS: k_walk_pt<BDPT_WALK_ST, BDPT_WALK_FT, BDPT_WALK_MINB, BDPT_TRAIT_LENS><<<g, threads, shm, ctx->stream>>>(J); break;
+      default: k_walk_pt<BDPT_WALK_ST, BDPT_WALK_FT, BDPT_WALK_MINB, 0><<<g, threads, shm, ctx->stream>>>(J); break;
     }
   } else {
     const unsigned g = (unsigned)((2 * J.B + threads - 1) / threads);
@@ -337,8 +345,8 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
     // (The persistent form wins even on one-node BVHs: 2.9 vs 4.9 ms per 2^24 samples.)
     const size_t shm = (size_t)J.ntop * 80;
     if ((ctx->spec & 4) && (ctx->traits & BDPT_TRAIT_TRIS)) {
-      const int c = ctx->shadow_ctas > 0 ? ctx->shadow_ctas : 10;
-      k_shadow_pt<10, BDPT_TRAIT_TRIS><<<ctx->sm_count * c, threads, shm, ctx->stream>>>(J);
+      const int c = ctx->shadow_ctas > 0 ? ctx->shadow_ctas : BDPT_SHADOW_MINB;
+      k_shadow_pt<BDPT_SHADOW_MINB, BDPT_TRAIT_TRIS><<<ctx->sm_count * c, threads, shm, ctx->stream>>>(J);
     } else {
       const int c = ctx->shadow_ctas > 0 ? ctx->shadow_ctas : 8;
       k_shadow_pt<8><<<ctx->sm_count * c, threads, shm, ctx->stream>>>(J);
