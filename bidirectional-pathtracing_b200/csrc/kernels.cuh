@@ -119,10 +119,18 @@ __device__ inline float mis_pow(const Job& J, float r) { return J.balance ? fabs
 // Per-lane subpath state.
 struct WalkState {
   Rng rng;
-  f3 prev_n, alpha, prev_f;
-  float prev_pdf, pdfeval_prev, D_prev, S_prev;
-  int kind, si, j, nv;
-  bool delta_prev, emis;
+  f3 prev_n;
+  f3 thr;   // alpha_{j-1} * f_{j-1} / pdf_{j-1}: alpha_j is this times the cosine at vertex j-1 (bidirection.cpp:66) — one
+            // vector instead of alpha, f and pdf: four registers less across the traversal loop
+  float pdfeval_prev, D_prev, S_prev;
+  // subpath index i = kind * B + si (kind 0 = eye, 1 = light) | bit 30: the previous vertex is a delta surface | bit 31: the
+  // last stored vertex is an emitter — and j, the vertex the current ray looks for (the subpath holds j - 1 so far): two
+  // registers where kind, si, j, nv and two flags took six
+  unsigned idx;
+  int j;
+  __device__ inline int i() const { return (int)(idx & 0x3fffffffu); }
+  __device__ inline bool delta_prev() const { return (idx & 0x40000000u) != 0u; }
+  __device__ inline bool emis() const { return (idx & 0x80000000u) != 0u; }
 };
 
 // New subpath: pinhole ray (raytrace_pixel, bidirection.cpp:517-524) or light emission
@@ -130,22 +138,22 @@ struct WalkState {
 template <int TR = 0>
 __device__ inline bool walk_begin(const Job& J, unsigned i, WalkState& W, Trav& T) {
   const bool lens = (TR & BDPT_TRAIT_LENS) && J.cam.lens_radius > 0.f;
-  W.kind = i >= (unsigned)J.B ? 1 : 0;
-  W.si = (int)i - W.kind * J.B;
+  const int kind = i >= (unsigned)J.B ? 1 : 0;
+  const int si = (int)i - kind * J.B;
   int x, y, sample;
-  if (!decode_sample(J, J.g0 + (unsigned long long)W.si, &x, &y, &sample)) { J.counts[i] = 0; return false; }
+  if (!decode_sample(J, J.g0 + (unsigned long long)si, &x, &y, &sample)) { J.counts[i] = 0; return false; }
   W.rng.begin(J.seed, (unsigned long long)y * (unsigned long long)J.cam.W + (unsigned long long)x,
-              (unsigned long long)sample, (uint32_t)W.kind);
-  W.prev_f = mk3(1.f); W.delta_prev = false; W.emis = false; W.nv = 1; W.j = 2;
+              (unsigned long long)sample, (uint32_t)kind);
+  W.idx = i; W.j = 2;
   f3 o, d;
-  if (W.kind == 0) {
+  if (kind == 0) {
     float sx = W.rng.uniform(), sy = W.rng.uniform();
     if (lens) {   // thin lens (extension): two more draws, the eye subpath starts on the lens
       const float u1 = W.rng.uniform(), u2 = W.rng.uniform();
       camera_generate_ray_lens(J.cam, ((float)x + sx) / (float)J.cam.W, ((float)y + sy) / (float)J.cam.H, u1, u2, &o, &d);
     } else
     camera_generate_ray(J.cam, ((float)x + sx) / (float)J.cam.W, ((float)y + sy) / (float)J.cam.H, &o, &d);
-    W.prev_n = d; W.alpha = mk3(1.f); W.prev_pdf = 1.f;
+    W.prev_n = d; W.thr = mk3(1.f);
     W.pdfeval_prev = 1.f; W.D_prev = 1.f; W.S_prev = 0.f;
     if (lens) {   // thin lens: the lens point can also be reached by a light subpath (t = 0), density 1 / lens area
       W.S_prev = 1.f; W.D_prev = 1.0f / (BDPT_PI * J.cam.lens_radius * J.cam.lens_radius);
@@ -157,12 +165,14 @@ __device__ inline bool walk_begin(const Job& J, unsigned i, WalkState& W, Trav& 
     float pA, pdir; f3 nl;
     f3 Le = light_sample_Le(J.sc, L, W.rng, &o, &d, &pA, &pdir, &nl);
     pA /= (float)J.sc.n_lights;
-    W.prev_n = nl; W.alpha = Le * (1.0f / pA); W.prev_pdf = pdir;
+    W.prev_n = nl;
+    const f3 alpha1 = Le * (1.0f / pA);
+    W.thr = alpha1 * (1.0f / pdir);
     W.pdfeval_prev = pdir; W.D_prev = pA; W.S_prev = 1.f;
-    size_t s1 = VSLOT(J, 1, 1, W.si);
+    size_t s1 = VSLOT(J, 1, 1, si);
     store_vertex(J, s1, make_float4(o.x, o.y, o.z, __int_as_float(-1)),
                  make_float4(nl.x, nl.y, nl.z, pA),
-                 make_float4(W.alpha.x, W.alpha.y, W.alpha.z, 1.f),
+                 make_float4(alpha1.x, alpha1.y, alpha1.z, 1.f),
                  make_float4(pdir, 0.f, 0.f, 1.f));
     T.begin(o, d, BDPT_EPS_F, INFINITY);
   }
@@ -202,14 +212,14 @@ __device__ inline void lens_strategy(const Job& J, const WalkState& W, f3 o, f3 
   const float A = BDPT_PI * c.lens_radius * c.lens_radius;
   const float cos_prev = fabsf(dot(W.prev_n, d));
   const float cos_u = dcl.z / norm(dcl);
-  const f3 contrib = W.alpha * W.prev_f * (cos_prev / W.prev_pdf) * (We / (A * cos_u));
+  const f3 contrib = W.thr * cos_prev * (We / (A * cos_u));
   if (!(norm(contrib) > BDPT_EPS_F)) return;
   float w = 1.f;
   if (!J.no_mis) {
     const float g0 = cos_prev / (dist * dist);
     const float ratio1 = (1.0f / A) / (W.pdfeval_prev * g0);          // p_1 / p_0
     const float r_s = cam_dir_pdf * g0 / W.D_prev;
-    const double winv = 1.0 + (double)mis_pow(J, ratio1) * ((double)((s >= 2 && W.delta_prev) ? 0.f : 1.f) + (double)mis_pow(J, r_s) * (double)W.S_prev);
+    const double winv = 1.0 + (double)mis_pow(J, ratio1) * ((double)((s >= 2 && W.delta_prev()) ? 0.f : 1.f) + (double)mis_pow(J, r_s) * (double)W.S_prev);
     w = (float)(1.0 / winv);
     if (!(w >= 0.f)) w = 0.f;
   }
@@ -223,9 +233,11 @@ template <int TR = 0>
 __device__ inline bool walk_shade(const Job& J, WalkState& W, Trav& T) {
   const DScene& sc = J.sc;
   const f3 o = T.o, d = T.d;
-  if ((TR & BDPT_TRAIT_LENS) && W.kind == 1 && J.cam.lens_radius > 0.f) lens_strategy(J, W, o, d, T.hit.leaf < 0 ? INFINITY : T.hit.t);
+  const int kind = W.i() >= J.B ? 1 : 0, si = W.i() - kind * J.B;
+  if ((TR & BDPT_TRAIT_LENS) && kind == 1 && J.cam.lens_radius > 0.f) lens_strategy(J, W, o, d, T.hit.leaf < 0 ? INFINITY : T.hit.t);
   if (T.hit.leaf < 0) {
-    if (sc.env_light < 0 || W.kind != 0) return false;   // (a LIGHT subpath's vertex on an emitter carries nothing: f = 0)
+    W.j--;   // (no vertex for this ray, unless the environment gives one below)
+    if (sc.env_light < 0 || kind != 0) return false;   // (a LIGHT subpath's vertex on an emitter carries nothing: f = 0)
     // The ray leaves the scene: it meets the environment's sphere (shading.cuh, "environment light"), whose surface
     // is an emitter — the vertex is stored like any other emissive end of a subpath, and the walk ends there.
     const Light L = load_light(sc, sc.env_light);
@@ -236,14 +248,15 @@ __device__ inline bool walk_shade(const Job& J, WalkState& W, Trav& T) {
     const f3 pe = o + d * te, ne = normalized(L.position - pe);
     const float cos_prev = fabsf(dot(W.prev_n, d));
     const float ge = cos_prev * fabsf(dot(ne, d)) / (te * te);
-    W.alpha = W.alpha * W.prev_f * (cos_prev / W.prev_pdf);
-    const float D_e = (W.kind == 0 && W.j == 2) ? 1.f : W.pdfeval_prev * ge;
-    float S_e = W.delta_prev ? 0.f : 1.f;
+    const f3 alpha = W.thr * cos_prev;
+    W.j++;
+    const float D_e = (kind == 0 && W.j == 2) ? 1.f : W.pdfeval_prev * ge;
+    float S_e = W.delta_prev() ? 0.f : 1.f;
     if (W.S_prev > 0.f) S_e += mis_pow(J, cosine_pdf(-dot(ne, d)) * ge / W.D_prev) * W.S_prev;
-    store_vertex(J, VSLOT(J, W.kind, W.j, W.si), make_float4(pe.x, pe.y, pe.z, __int_as_float(sc.n_materials)),
-                 make_float4(ne.x, ne.y, ne.z, D_e), make_float4(W.alpha.x, W.alpha.y, W.alpha.z, clampS(S_e)),
+    store_vertex(J, VSLOT(J, kind, W.j, si), make_float4(pe.x, pe.y, pe.z, __int_as_float(sc.n_materials)),
+                 make_float4(ne.x, ne.y, ne.z, D_e), make_float4(alpha.x, alpha.y, alpha.z, clampS(S_e)),
                  make_float4(-d.x, -d.y, -d.z, 1.f));
-    W.nv = W.j; W.emis = true;
+    W.idx |= 0x80000000u;
     return false;
   }
   f3 n, hit_p; int prim, mat;
@@ -259,7 +272,7 @@ __device__ inline bool walk_shade(const Job& J, WalkState& W, Trav& T) {
   // bidirection.cpp:64-69
   const float cos_prev = fabsf(dot(W.prev_n, d));
   const float g = cos_prev * fabsf(dot(n, d)) / (t * t);
-  W.alpha = W.alpha * W.prev_f * (cos_prev / W.prev_pdf);
+  const f3 alpha = W.thr * cos_prev;
 
   // roulette (off in the reference: bidirection.cpp:80; the disabled rule is :87-93)
   float p_keep = 1.f;
@@ -267,26 +280,26 @@ __device__ inline bool walk_shade(const Job& J, WalkState& W, Trav& T) {
 
   // MIS cache
   const bool delta_j = type_is_delta(M.type);
-  const float D_j = (W.kind == 0 && W.j == 2) ? 1.f : W.pdfeval_prev * g;
+  const float D_j = (kind == 0 && W.j == 2) ? 1.f : W.pdfeval_prev * g;
   const float D_rev = bsdf_pdf_mis(M, wi, w_out) * p_keep * g;  // density of (j -> j-1) as the chains use it
-  float S_j = (delta_j || W.delta_prev) ? 0.f : 1.f;
+  float S_j = (delta_j || W.delta_prev()) ? 0.f : 1.f;
   if (W.S_prev > 0.f) S_j += mis_pow(J, D_rev / W.D_prev) * W.S_prev;
   S_j = clampS(S_j);
 
-  size_t sl = VSLOT(J, W.kind, W.j, W.si);
+  size_t sl = VSLOT(J, kind, W.j, si);
   store_vertex(J, sl, make_float4(hit_p.x, hit_p.y, hit_p.z, __int_as_float(mat)),
                make_float4(n.x, n.y, n.z, D_j),
-               make_float4(W.alpha.x, W.alpha.y, W.alpha.z, S_j),
+               make_float4(alpha.x, alpha.y, alpha.z, S_j),
                make_float4(-d.x, -d.y, -d.z, p_keep));
-  W.nv = W.j;
-  W.emis = M.type == BDPT_MAT_EMISSION;
+  W.idx = (W.idx & 0x7fffffffu) | (M.type == BDPT_MAT_EMISSION ? 0x80000000u : 0u);
   if (W.j >= J.m + 1) return false;
   if (J.roulette && !(W.rng.uniform() < p_keep)) return false;
   if (is_zero(f)) return false;  // throughput is exactly zero from here on: later vertices add nothing
 
   W.pdfeval_prev = bsdf_pdf_mis(M, w_out, wi) * p_keep;
-  W.prev_f = f; W.prev_n = n; W.prev_pdf = pdf * p_keep;
-  W.D_prev = D_j; W.S_prev = S_j; W.delta_prev = delta_j;
+  W.thr = alpha * f * (1.0f / (pdf * p_keep)); W.prev_n = n;
+  W.D_prev = D_j; W.S_prev = S_j;
+  W.idx = (W.idx & 0xbfffffffu) | (delta_j ? 0x40000000u : 0u);
   W.j++;
   T.begin(hit_p, wi_world, BDPT_EPS_F, INFINITY);
   return true;
@@ -295,7 +308,7 @@ __device__ inline bool walk_shade(const Job& J, WalkState& W, Trav& T) {
 // what k_connect reads per subpath: its length and whether its LAST vertex is an emitter.  (An EmissionBSDF
 // returns f = 0, bsdf.cpp:106-110, so the walk ends there: no other vertex of a subpath can be one.)
 __device__ inline void walk_end(const Job& J, const WalkState& W) {
-  J.counts[W.kind * J.B + W.si] = W.nv | (W.emis ? 0x100 : 0);
+  J.counts[W.i()] = W.j | (W.emis() ? 0x100 : 0);
 }
 
 // One subpath per lane, start to end.  Used for scenes whose BVH has at most 8 nodes (nothing diverges there).

@@ -22,8 +22,7 @@ namespace bdpt {
 struct Hit {
   float t;
   int leaf;  // index into the leaf-ordered primitive arrays, -1 = miss
-  float b1, b2;
-};
+};   // (no barycentrics: finish_hit computes them for the one winner — two registers less in the traversal loops)
 
 // byte k of w as the float 2^15 + bb, without an int->float conversion: PRMT builds 0x4700bb00.
 // The box test folds the 2^15 into its per-axis constant, so a quantised plane costs one PRMT and
@@ -37,8 +36,7 @@ __device__ inline float qbyte(uint32_t w, int k, uint32_t bias_bits) {   // bias
 // Intersect one leaf primitive; returns true and shrinks tmax on an accepted hit.  (Record layouts: bvh_gpu.cuh,
 // make_leaf_record.)
 template <int TR = 0>
-__device__ inline bool intersect_prim(const float4* __restrict__ prims, int k, f3 o, f3 d, float tmin, float& tmax,
-                                      float& b1o, float& b2o) {
+__device__ inline bool intersect_prim(const float4* __restrict__ prims, int k, f3 o, f3 d, float tmin, float& tmax) {
   float4 c, a;
 #if BDPT_PRIM_Q == 4
   ld256nc(prims + BDPT_PRIM_Q * k, &c, &a);
@@ -56,7 +54,7 @@ __device__ inline bool intersect_prim(const float4* __restrict__ prims, int k, f
     const float b1 = fmaf(a.x, px, fmaf(a.y, py, fmaf(a.z, pz, a.w)));
     const float b2 = fmaf(b.x, px, fmaf(b.y, py, fmaf(b.z, pz, b.w)));
     if (t >= tmin && t <= tmax && b1 >= 0.f && b2 >= 0.f && b1 + b2 <= 1.f) {
-      tmax = t; b1o = b1; b2o = b2;
+      tmax = t;
       return true;
     }
     return false;
@@ -71,7 +69,7 @@ __device__ inline bool intersect_prim(const float4* __restrict__ prims, int k, f
   float t1 = (-hb - sd) * ia, t2 = (-hb + sd) * ia, t = -1.f;
   if (t1 >= tmin && t1 <= tmax) t = t1;
   else if (t2 >= tmin && t2 <= tmax) t = t2;
-  if (t > 0.f) { tmax = t; b1o = 0.f; b2o = 0.f; return true; }
+  if (t > 0.f) { tmax = t; return true; }
   return false;
 }
 
@@ -90,7 +88,7 @@ struct Trav {
 
   __device__ inline void begin(f3 o_, f3 d_, float tmin_, float tmax_) {
     o = o_; d = d_; tmin = tmin_;
-    hit.t = tmax_; hit.leaf = -1; hit.b1 = 0.f; hit.b2 = 0.f;
+    hit.t = tmax_; hit.leaf = -1;
     oct = (d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u);
     // MUFU.RCP (<= 2 ulp): the reciprocals only feed the box cull, whose slack factor below covers them
     idir.x = rcp_fast(fabsf(d.x) > 1e-20f ? d.x : copysignf(1e-20f, d.x));
@@ -188,7 +186,7 @@ struct Trav {
       int i = __ffs(tris) - 1;
       tris &= tris - 1u;
       int k = pbase + i;
-      if (intersect_prim<TR>(sc.prims, k, o, d, tmin, hit.t, hit.b1, hit.b2)) {
+      if (intersect_prim<TR>(sc.prims, k, o, d, tmin, hit.t)) {
         hit.leaf = k;
         if (ANY_HIT) return true;
       }
@@ -262,15 +260,20 @@ __device__ inline void finish_hit(const DScene& sc, Hit& h, f3 o, f3 d, f3* n, i
     const double t = (s2x * e2x + s2y * e2y + s2z * e2z) * inv;
     const double b1 = (s1x * sx + s1y * sy + s1z * sz) * inv;
     const double b2 = (s2x * dx + s2y * dy + s2z * dz) * inv;
+    float hb1, hb2;
     if (t == t && fabs(t - (double)h.t) <= 1e-3 * fabs((double)h.t)) {  // sanity: same root
-      h.t = (float)t; h.b1 = (float)b1; h.b2 = (float)b2;
+      h.t = (float)t; hb1 = (float)b1; hb2 = (float)b2;
       *hit_p = mk3((float)(ox + dx * t), (float)(oy + dy * t), (float)(oz + dz * t));
     } else {
+      // (never seen on the fixture scenes) keep the fp32 hit: its barycentrics from the record's u and v rows
       *hit_p = o + d * h.t;
+      const float4 ru = ldg4(sc.prims + BDPT_PRIM_Q * h.leaf + 1), rv = ldg4(sc.prims + BDPT_PRIM_Q * h.leaf + 2);
+      hb1 = fmaf(ru.x, hit_p->x, fmaf(ru.y, hit_p->y, fmaf(ru.z, hit_p->z, ru.w)));
+      hb2 = fmaf(rv.x, hit_p->x, fmaf(rv.y, hit_p->y, fmaf(rv.z, hit_p->z, rv.w)));
     }
     const float4 n3 = ldg4(sc.shading + 3 * h.leaf + 2);
-    float b0 = 1.f - h.b1 - h.b2;
-    f3 nn = mk3(n1.x, n1.y, n1.z) * b0 + h.b1 * mk3(n2.x, n2.y, n2.z) + h.b2 * mk3(n3.x, n3.y, n3.z);
+    float b0 = 1.f - hb1 - hb2;
+    f3 nn = mk3(n1.x, n1.y, n1.z) * b0 + hb1 * mk3(n2.x, n2.y, n2.z) + hb2 * mk3(n3.x, n3.y, n3.z);
     *n = normalized(nn);
   } else {
     const double2 g0 = __ldg((const double2*)g), g1 = __ldg((const double2*)g + 1);
