@@ -327,18 +327,19 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
     }
   }
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 1), ctx->stream);
-  // k_connect at 6 CTAs/SM (80 registers; the Lambert build spills 32 bytes, the generic one ~220): measured on B200
-  // per 2^24 samples — CBbunny 4.00 ms (bounds 4 / 5: 4.24, 8: 6.80, 3: 4.95), CBgems m=16 1.54 (5: 1.63, 8: 2.41),
-  // CBspheres 6.30 (5: 6.60).  BDPT_CONNECT_MINB overrides the bound only, never the trait.
+  // k_connect at 5 CTAs/SM (96 registers, nothing spilled).  Re-measured after the division / square-root change made
+  // the kernel shorter — per 2^24 samples, bounds 5 / 6 / 4 / 8: CBbunny4 3.47 / 3.51 / 3.85 / 4.38 ms, CBspheres 3.69 / 3.95
+  // / 4.14, glass bunny 3.69 / 3.93 / 4.13, CBgems m=16 1.41 / 1.57 / 1.54 (before it: 6 won, 4.00 against 4.24 on CBbunny).
+  // BDPT_CONNECT_MINB overrides the bound only, never the trait.
   const unsigned cgrid = (unsigned)((J.B + BDPT_CONNECT_NT - 1) / BDPT_CONNECT_NT);
   // a sample pushes at most (m+1)^2 shadow rays (t = 1..m+1, s = 1..m+1): a block's segment cannot overflow
   J.seg_cap = (unsigned)(BDPT_CONNECT_NT * (J.m + 1) * (J.m + 1));
   J.chunk_cap = (unsigned)std::min<size_t>(ctx->cap_chunks, 0xffffffffu);
   const int ctr = (!TRACE && (ctx->spec & 2)) ? (ctx->traits & (BDPT_TRAIT_LAMBERT | BDPT_TRAIT_NOMF)) : 0;
-  if (lens) launch_connect<TRACE, BDPT_TRAIT_LENS>(ctx, J, cgrid, ctx->connect_minb ? ctx->connect_minb : 6);
-  else if (ctr & BDPT_TRAIT_LAMBERT) launch_connect<TRACE, BDPT_TRAIT_LAMBERT>(ctx, J, cgrid, ctx->connect_minb ? ctx->connect_minb : 6);
-  else if (ctr & BDPT_TRAIT_NOMF) launch_connect<TRACE, BDPT_TRAIT_NOMF>(ctx, J, cgrid, ctx->connect_minb ? ctx->connect_minb : 6);
-  else launch_connect<TRACE, 0>(ctx, J, cgrid, ctx->connect_minb ? ctx->connect_minb : 6);
+  if (lens) launch_connect<TRACE, BDPT_TRAIT_LENS>(ctx, J, cgrid, ctx->connect_minb ? ctx->connect_minb : 5);
+  else if (ctr & BDPT_TRAIT_LAMBERT) launch_connect<TRACE, BDPT_TRAIT_LAMBERT>(ctx, J, cgrid, ctx->connect_minb ? ctx->connect_minb : 5);
+  else if (ctr & BDPT_TRAIT_NOMF) launch_connect<TRACE, BDPT_TRAIT_NOMF>(ctx, J, cgrid, ctx->connect_minb ? ctx->connect_minb : 5);
+  else launch_connect<TRACE, 0>(ctx, J, cgrid, ctx->connect_minb ? ctx->connect_minb : 5);
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 2), ctx->stream);
   {
     // triangles only: 48 registers (28 B of spills) and 10 CTAs/SM; with the sphere test compiled in, 64 and 8.
