@@ -38,6 +38,9 @@ thread_local std::string g_create_error = "";
 #define BDPT_SHADOW_MINB 9    // resident CTAs/SM the triangle build of k_shadow_pt is compiled for: 56 registers, nothing spilled
                               // (10: 48 registers, 36 B of spills in the hot loop, +3.8 %; 8: +0.2 %; 11: +15 %)
 #endif
+#ifndef BDPT_SHADOW_GEN_MINB
+#define BDPT_SHADOW_GEN_MINB 9   // ... and the build with the sphere test compiled in (also 56 registers, nothing spilled; 8: +2.3 % on CBspheres)
+#endif
 #define BDPT_SMALL_SCENE 1024u   // primitives up to which the host builds the (same) PLOC tree; crossover measured near 1,500
 
 struct BdptContext {
@@ -349,8 +352,8 @@ int run_batch(BdptContext* ctx, Job& J, long evbase) {
       const int c = ctx->shadow_ctas > 0 ? ctx->shadow_ctas : BDPT_SHADOW_MINB;
       k_shadow_pt<BDPT_SHADOW_MINB, BDPT_TRAIT_TRIS><<<ctx->sm_count * c, threads, shm, ctx->stream>>>(J);
     } else {
-      const int c = ctx->shadow_ctas > 0 ? ctx->shadow_ctas : 8;
-      k_shadow_pt<8><<<ctx->sm_count * c, threads, shm, ctx->stream>>>(J);
+      const int c = ctx->shadow_ctas > 0 ? ctx->shadow_ctas : BDPT_SHADOW_GEN_MINB;
+      k_shadow_pt<BDPT_SHADOW_GEN_MINB><<<ctx->sm_count * c, threads, shm, ctx->stream>>>(J);
     }
   }
   if (evbase >= 0) cudaEventRecord(get_event(ctx, evbase + 3), ctx->stream);
