@@ -84,6 +84,23 @@ def load_fixture(fixture):
     return fs.load(os.path.join(ROOT, "tests", "golden", "scenes", fixture + ".fscene.gz"))
 
 
+def pinned_scene(scene):
+    """The same scene with its arrays in page-locked host memory (what the e2e contract asks the step's inputs to be in):
+    bdpt_upload_scene's H2D copy of the primitives then runs at PCIe rate instead of through the driver's staging buffer."""
+    import numpy as np
+    import torch
+    from bdpt import flatscene as fs
+
+    def pin(a):
+        a = np.ascontiguousarray(a)
+        if a.nbytes == 0:
+            return a
+        t = torch.from_numpy(a.view(np.uint8).reshape(-1)).pin_memory()
+        return t.numpy().view(a.dtype).reshape(a.shape)
+    out = fs.FlatScene(pin(scene.camera), pin(scene.materials), pin(scene.lights), pin(scene.prims))
+    return out
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -255,7 +272,7 @@ def algorithmic_bytes(st):
 def measure_config(api, shard, torch, dist, cfg, args, rank, world, local, stream, steps, warmup, e2e_steps):
     """Renders cfg's frame `steps` times resident and `e2e_steps` times end to end; returns the numbers of the line."""
     fixture, dae, W, H, spp, m, roulette, desc = cfg
-    scene = load_fixture(fixture)
+    scene = pinned_scene(load_fixture(fixture))   # host inputs in pinned memory (the e2e step copies them up every time)
     first, n_mine = shard.shard_samples(spp, rank, world)
     R = api.Renderer(local, ns_aa=spp, max_ray_depth=m, seed=0, roulette=bool(roulette))
     R.set_stream(stream.cuda_stream)

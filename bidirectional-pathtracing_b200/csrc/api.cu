@@ -455,15 +455,21 @@ int build_scene_on_device(BdptContext* ctx, const BdptPrim* prims, uint32_t n_pr
   int n_upper = N; uint32_t rounds = 0;
   int radius = BDPT_PLOC_RADIUS;
   if (const char* e = getenv("BDPT_PLOC_RADIUS")) radius = std::max(1, std::min(256, atoi(e)));   // tuning only
+  bool tail = false;
   while (n_upper > 1) {
+    if (n_upper <= 1024) {   // the rest in one launch (bvh_gpu.cuh, k_ploc_tail); its round count comes back with the emission's
+      k_ploc_tail<<<1, 1024, 0, st>>>(ctr, cluster, clo, chi, T, radius);
+      CK(cudaMemcpyAsync(ctx->h_bvh + 12, ctr + 3, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+      ctx->stats.kernel_launches += 1; tail = true;
+      break;
+    }
     for (int r = 0; r < 4; r++) {
       const int g = (n_upper + BDPT_PLOC_BLOCK - 1) / BDPT_PLOC_BLOCK;
       k_ploc_nearest<<<g, BDPT_PLOC_BLOCK, 0, st>>>(ctr, clo, chi, nn, radius);
       k_ploc_merge<<<g, BDPT_PLOC_BLOCK, 0, st>>>(ctr, nn, cluster, clo, chi, T, out_id, olo, ohi, keep, bcount);
       k_ploc_scan<<<1, 1024, 0, st>>>(ctr, bcount, boff);
       k_ploc_scatter<<<g, BDPT_PLOC_BLOCK, 0, st>>>(ctr, keep, boff, out_id, olo, ohi, cluster, clo, chi);
-      k_ploc_advance<<<1, 1, 0, st>>>(ctr);
-      ctx->stats.kernel_launches += 5; rounds++;
+      ctx->stats.kernel_launches += 4; rounds++;
     }
     CK(cudaMemcpyAsync(ctx->h_bvh + 8, ctr, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -472,7 +478,7 @@ int build_scene_on_device(BdptContext* ctx, const BdptPrim* prims, uint32_t n_pr
     if (n_now == n_upper && n_now > 1 && rounds > 4096) return fail(ctx, BDPT_ERR_CUDA, "device BVH build does not converge");
     n_upper = n_now;
   }
-  ctx->bvh_rounds = rounds;
+  ctx->bvh_rounds = rounds;   // (+ the tail's, below)
   // collapse DP, bottom-up
   CK(cudaMemsetAsync(visit, 0, n2 * 4, st));
   WideParams P; P.max_leaf = 3; P.prim_cost = 0.8f;
@@ -495,6 +501,7 @@ int build_scene_on_device(BdptContext* ctx, const BdptPrim* prims, uint32_t n_pr
     cur ^= 1;
   }
   if (ctx->h_bvh[9] != (unsigned)N) return fail(ctx, BDPT_ERR_CUDA, "device BVH build: not every primitive reached a leaf");
+  if (tail) ctx->bvh_rounds += ctx->h_bvh[12];   // (copied back before the emission's synchronisations)
   *n_nodes = ctx->h_bvh[8]; *depth = levels;
   k_bvh_records<<<G, TB, 0, st>>>(d_raw, prim_order, N, ctx->d_prims, ctx->d_shading, ctx->d_prims64);
   ctx->stats.kernel_launches += 1;

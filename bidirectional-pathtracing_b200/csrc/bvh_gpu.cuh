@@ -94,7 +94,8 @@ __global__ void k_bvh_leaves(const float4* blo, const float4* bhi, const uint32_
   cluster[k] = k; clo[k] = a; chi[k] = b;
 }
 
-// ---- one PLOC round.  ctr: [0] clusters now  [1] clusters after this round  [2] next free node id
+// ---- one PLOC round.  ctr: [0] clusters now  [1] clusters after this round  [2] next free node id  [3] rounds of the tail
+// kernel  [4..6] the emission's counters  [8] clusters at the start of the round (for its scatter)
 __global__ void k_ploc_nearest(const unsigned* ctr, const float4* clo, const float4* chi, int* nn, int radius) {
   const int n = (int)ctr[0];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -164,13 +165,14 @@ __global__ void __launch_bounds__(1024) k_ploc_scan(unsigned* ctr, const unsigne
     if (threadIdx.x == 0) s_carry += s_w[31];
     __syncthreads();
   }
-  if (threadIdx.x == 0) ctr[1] = n >= 2 ? s_carry : (unsigned)n;
+  // the round's output count becomes the next round's input; the scatter that follows reads this round's from ctr[8]
+  if (threadIdx.x == 0) { const unsigned nn = n >= 2 ? s_carry : (unsigned)n; ctr[8] = (unsigned)n; ctr[1] = nn; ctr[0] = nn; }
 }
 
 __global__ void __launch_bounds__(BDPT_PLOC_BLOCK) k_ploc_scatter(const unsigned* ctr, const unsigned char* keep, const unsigned* boff, const int* out_id,
                                                                    const float4* olo, const float4* ohi, int* cluster, float4* clo, float4* chi) {
   __shared__ unsigned s_w[BDPT_PLOC_BLOCK / 32];
-  const int n = (int)ctr[0];
+  const int n = (int)ctr[8];   // (this round's input count: k_ploc_scan has already moved ctr[0] on)
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (n < 2) return;   // (whole grid: nothing to do, the array is final)
   const bool stay = i < n && keep[i];
@@ -186,8 +188,65 @@ __global__ void __launch_bounds__(BDPT_PLOC_BLOCK) k_ploc_scatter(const unsigned
   }
 }
 
-// after scatter: the round's output becomes the next round's input
-__global__ void k_ploc_advance(unsigned* ctr) { ctr[0] = ctr[1]; }
+// The last rounds in one launch.  PLOC's cluster count falls fast at first and slowly at the end (CBbunny4: 114 k -> 1 k in
+// ~28 of its 56 rounds; a scene of 252 primitives alone takes 24): once at most 1,024 clusters are left, one block keeps the
+// cluster array in shared memory and runs the remaining rounds — the same nearest / mutual-merge / order-preserving
+// compaction steps as the kernels above, so the same tree — instead of five tiny launches per round.
+// ctr[3] receives the number of rounds it ran.
+__global__ void __launch_bounds__(1024) k_ploc_tail(unsigned* ctr, int* cluster, float4* clo, float4* chi, DevTree T, int radius) {
+  __shared__ float4 s_lo[1024], s_hi[1024];
+  __shared__ int s_id[1024], s_nn[1024];
+  __shared__ unsigned s_w[32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int n = (int)ctr[0];
+  if (tid < n) { s_id[tid] = cluster[tid]; s_lo[tid] = clo[tid]; s_hi[tid] = chi[tid]; }
+  unsigned rounds = 0;
+  __syncthreads();
+  while (n >= 2) {
+    if (tid < n) s_nn[tid] = ploc_nearest(tid, n, (const float*)s_lo, (const float*)s_hi, radius);
+    __syncthreads();
+    bool stay = false;
+    int id = 0;
+    float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = lo;
+    if (tid < n) {
+      const int j = s_nn[tid];
+      const bool mutual = s_nn[j] == tid;
+      stay = !(mutual && tid > j);
+      if (stay) {
+        id = s_id[tid]; lo = s_lo[tid]; hi = s_hi[tid];
+        if (mutual) {
+          const int cj = s_id[j];
+          const float4 l2 = s_lo[j], h2 = s_hi[j];
+          lo = make_float4(fminf(lo.x, l2.x), fminf(lo.y, l2.y), fminf(lo.z, l2.z), 0.f);
+          hi = make_float4(fmaxf(hi.x, h2.x), fmaxf(hi.y, h2.y), fmaxf(hi.z, h2.z), 0.f);
+          const int ci = id;
+          id = (int)atomicAdd(ctr + 2, 1u);
+          T.lo[id] = lo; T.hi[id] = hi; T.left[id] = ci; T.right[id] = cj; T.parent[id] = -1;
+          T.count[id] = T.count[ci] + T.count[cj];
+          T.parent[ci] = id; T.parent[cj] = id;
+        }
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, stay);
+    if (lane == 0) s_w[wid] = (unsigned)__popc(m);
+    __syncthreads();   // (also: every read of the round's arrays is done)
+    if (wid == 0) {
+      unsigned w = s_w[lane];
+      for (int d = 1; d < 32; d <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, w, d); if (lane >= d) w += y; }
+      s_w[lane] = w;   // inclusive over warps
+    }
+    __syncthreads();
+    if (stay) {
+      const unsigned pos = (wid ? s_w[wid - 1] : 0u) + (unsigned)__popc(m & ((1u << lane) - 1u));
+      s_id[pos] = id; s_lo[pos] = lo; s_hi[pos] = hi;
+    }
+    n = (int)s_w[31];
+    rounds++;
+    __syncthreads();
+  }
+  if (tid < n) { cluster[tid] = s_id[tid]; clo[tid] = s_lo[tid]; chi[tid] = s_hi[tid]; }
+  if (tid == 0) { ctr[0] = (unsigned)n; ctr[1] = (unsigned)n; ctr[3] = rounds; }
+}
 
 // ---- bottom-up collapse DP: one thread per leaf walks up; the second thread to arrive at a node computes it
 __global__ void k_bvh_collapse_dp(DevTree T, int n_leaves, WideParams P, float* C, uint8_t* split, uint8_t* is_leaf, unsigned* visit) {

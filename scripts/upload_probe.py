@@ -7,6 +7,8 @@ from bdpt import api
 import bench
 for name in sys.argv[1:]:
     sc = bench.load_fixture(name)
+    if os.environ.get("PROBE_PINNED"):
+        sc = bench.pinned_scene(sc)
     R = api.Renderer(0)
     ts = []
     for i in range(6):
