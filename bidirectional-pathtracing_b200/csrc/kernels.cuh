@@ -312,8 +312,13 @@ __device__ inline void walk_end(const Job& J, const WalkState& W) {
 }
 
 // One subpath per lane, start to end.  Used for scenes whose BVH has at most 8 nodes (nothing diverges there).
+// (compiled for 7 CTAs/SM, 72 registers: 5.59 ms per 2^24 samples on CBspheres; 6 / 8: 5.67; the 95 registers the compiler
+// takes without a bound — 5 CTAs —: 5.94)
+#ifndef BDPT_KWALK_MINB
+#define BDPT_KWALK_MINB 7
+#endif
 template <int TR = 0>
-__global__ void __launch_bounds__(128) k_walk(const __grid_constant__ Job J) {
+__global__ void __launch_bounds__(128, BDPT_KWALK_MINB) k_walk(const __grid_constant__ Job J) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;   // whole warps are in or out: 2B is a multiple of 32
   if (i >= 2u * (unsigned)J.B) return;
   WalkState W; Trav T;
