@@ -79,8 +79,11 @@ struct BdptContext {
   DCamera cam{};
   // un-normalised accumulators: ONE allocation of 2 * W * H float4 {r, g, b, -}, eye image first, light image second,
   // so that a multi-GPU frame is reduced with a single collective (bdpt_reduce) and a splat is one 16-byte reduction
+  // The kernels' reductions go to a second pair (acc_batch) that k_fold adds to `acc` after every batch with a
+  // compensation term (acc_comp): all three live in the one allocation, `acc` first.
   float4* acc = nullptr;
   float4 *acc_eye = nullptr, *acc_light = nullptr;
+  float4 *acc_comp = nullptr, *acc_batch = nullptr;
   float* resolve_tmp = nullptr;
   uint8_t* rgba_tmp = nullptr;
   int ns_last = 1;
@@ -263,7 +266,7 @@ void fill_job(BdptContext* ctx, const BdptRenderParams* p, Job* J) {
   J->cam.lens_radius = ctx->lens_radius; J->cam.focal_dist = ctx->focal_dist;
   J->v0 = ctx->v0; J->counts = ctx->counts;
   J->q0 = ctx->q0; J->q2 = ctx->q2; J->qctr = ctx->qctr; J->chunks = ctx->chunks;
-  J->acc_eye = ctx->acc_eye; J->acc_light = ctx->acc_light; J->stats = ctx->d_stats; J->dbg = nullptr;
+  J->acc_eye = ctx->acc_batch; J->acc_light = ctx->acc_batch + (size_t)ctx->W * ctx->H; J->stats = ctx->d_stats; J->dbg = nullptr;
   // the walk stores a vertex before it tests the depth (bidirection.cpp:82-86): m = 0 behaves as m = 1
   J->seed = p->seed; J->m = std::max(1, p->max_ray_depth); J->first_sample = p->first_sample;
   const bool cell = ctx->cell[2] > 0;
@@ -753,10 +756,10 @@ int bdpt_set_frame(BdptContext* ctx, int width, int height) {
     CK(cudaStreamSynchronize(ctx->stream));
     // no frame is held until every allocation below has succeeded
     ctx->W = ctx->H = 0;
-    dfree(ctx->acc); ctx->acc_eye = ctx->acc_light = nullptr;
+    dfree(ctx->acc); ctx->acc_eye = ctx->acc_light = ctx->acc_comp = ctx->acc_batch = nullptr;
     dfree(ctx->resolve_tmp); dfree(ctx->rgba_tmp);
     const size_t npix = (size_t)width * height;
-    cudaError_t e = cudaMalloc(&ctx->acc, 2 * npix * sizeof(float4));
+    cudaError_t e = cudaMalloc(&ctx->acc, 6 * npix * sizeof(float4));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->resolve_tmp, npix * 3 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->rgba_tmp, npix * 4);
     if (e != cudaSuccess) {
@@ -764,6 +767,7 @@ int bdpt_set_frame(BdptContext* ctx, int width, int height) {
       return fail(ctx, BDPT_ERR_CUDA, std::string("frame buffers: ") + cudaGetErrorString(e));
     }
     ctx->acc_eye = ctx->acc; ctx->acc_light = ctx->acc + npix;
+    ctx->acc_comp = ctx->acc + 2 * npix; ctx->acc_batch = ctx->acc + 4 * npix;
     ctx->W = width; ctx->H = height;
     ctx->cell[0] = ctx->cell[1] = ctx->cell[2] = ctx->cell[3] = 0;
   }
@@ -791,7 +795,7 @@ int bdpt_clear(BdptContext* ctx) {
   if (!ctx) return BDPT_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   if (ctx->acc && ctx->W > 0)
-    CK(cudaMemsetAsync(ctx->acc, 0, 2 * (size_t)ctx->W * ctx->H * sizeof(float4), ctx->stream));
+    CK(cudaMemsetAsync(ctx->acc, 0, 6 * (size_t)ctx->W * ctx->H * sizeof(float4), ctx->stream));
   if (ctx->d_stats) CK(cudaMemsetAsync(ctx->d_stats, 0, 4 * sizeof(unsigned long long), ctx->stream));
   BdptStats z{};
   z.ms_bvh_build = ctx->ms_bvh_build; z.bvh_nodes = ctx->bvh_nodes;
@@ -843,6 +847,10 @@ int bdpt_render(BdptContext* ctx, const BdptRenderParams* p) {
     J.k0 = (unsigned int)(J.g0 / (unsigned long long)npix_pad); J.p0 = (unsigned int)(J.g0 % (unsigned long long)npix_pad);
     rc = run_batch<false>(ctx, J, b < (unsigned long long)timed ? 2 + 4 * (long)b : -1);
     if (rc) return rc;
+    // the batch's splats join the frame's sums (compensated: kernels.cuh, k_fold)
+    const size_t nacc = 2 * (size_t)ctx->W * ctx->H;
+    k_fold<<<(unsigned)((nacc + 255) / 256), 256, 0, ctx->stream>>>(ctx->acc, ctx->acc_comp, ctx->acc_batch, nacc);
+    ctx->stats.kernel_launches += 1;
   }
   CK(cudaMemcpyAsync(ctx->h_qctr, ctx->qctr, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaEventRecord(e1, ctx->stream));

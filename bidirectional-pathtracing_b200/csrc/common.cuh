@@ -158,12 +158,16 @@ __device__ inline float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0,
 
 // 32-byte read-only loads (LDG.E.256.CONSTANT, sm_100): one L1 wavefront per lane where two 16-byte loads take two — the
 // traversal kernels run the L1 data pipe at 62-77 % of its wavefront peak (profiles/README.md, r02d)
+// (BDPT_HINT_SCENE: an L2 qualifier for the scene's records, measured in DESIGN.md §4)
+#ifndef BDPT_HINT_SCENE
+#define BDPT_HINT_SCENE ""
+#endif
 __device__ inline void ld256nc(const uint4* p, uint4* a, uint4* b) {
-  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+  asm volatile("ld.global.nc" BDPT_HINT_SCENE ".v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(a->x), "=r"(a->y), "=r"(a->z), "=r"(a->w), "=r"(b->x), "=r"(b->y), "=r"(b->z), "=r"(b->w) : "l"(p));
 }
 __device__ inline void ld256nc(const float4* p, float4* a, float4* b) {
-  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+  asm volatile("ld.global.nc" BDPT_HINT_SCENE ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=f"(a->x), "=f"(a->y), "=f"(a->z), "=f"(a->w), "=f"(b->x), "=f"(b->y), "=f"(b->z), "=f"(b->w) : "l"(p));
 }
 __device__ inline float4 ldg4(const float4* p) { return __ldg(p); }

@@ -90,19 +90,44 @@ __device__ inline bool decode_sample(const Job& J, unsigned long long g, int* x,
 // float4 index of the first quarter of the 64-byte record of vertex j of subpath (kind, i)
 #define VSLOT(J, kind, j, i) (4 * ((size_t)((kind) * ((J).m + 1) + ((j)-1)) * (size_t)(J).B + (size_t)(i)))
 
-// 32-byte global accesses (LDG.256 / STG.256, sm_100): half of a vertex record per instruction
-__device__ inline void ld256(const float4* p, float4* a, float4* b) {
-  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=f"(a->x), "=f"(a->y), "=f"(a->z), "=f"(a->w), "=f"(b->x), "=f"(b->y), "=f"(b->z), "=f"(b->w) : "l"(p));
-}
-__device__ inline void st256(float4* p, float4 a, float4 b) {
-  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-               :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
-}
+// 32-byte global accesses (LDG.256 / STG.256, sm_100): half of a vertex record per instruction.  The vertex records and
+// the shadow queue are written once and read once, gigabytes per batch, next to a scene (nodes, primitives) that every
+// ray re-reads from L1 / L2: their accesses carry cache qualifiers, one macro per site so that each can be measured
+// ("cache qualifiers").  Defaults = the measured optimum on B200:
+//   vertex stores (k_walk*)      L1::no_allocate + L2::evict_first   walk -3.4 % (the records no longer push the scene out of L2)
+//   vertex loads  (k_connect)    L1::no_allocate                     connect -1.8 % (with L2::evict_first: +4.4 %, the kernel's own L2 prefetch is lost)
+//   queue stores  (k_connect)    L1::no_allocate + L2::evict_first   connect -0.9 %
+//   queue loads   (k_shadow_pt)  L1::no_allocate
+#ifndef BDPT_HINT_VST
+#define BDPT_HINT_VST ".L1::no_allocate.L2::evict_first"
+#endif
+#ifndef BDPT_HINT_VLD
+#define BDPT_HINT_VLD ".L1::no_allocate"
+#endif
+#ifndef BDPT_HINT_QST
+#define BDPT_HINT_QST ".L1::no_allocate.L2::evict_first"
+#endif
+#ifndef BDPT_HINT_QLD
+#define BDPT_HINT_QLD ".L1::no_allocate"
+#endif
+#define BDPT_DEF_LD256(name, hint)                                                                                          \
+  __device__ inline void name(const float4* p, float4* a, float4* b) {                                                      \
+    asm volatile("ld.global" hint ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                                                \
+                 : "=f"(a->x), "=f"(a->y), "=f"(a->z), "=f"(a->w), "=f"(b->x), "=f"(b->y), "=f"(b->z), "=f"(b->w) : "l"(p)); \
+  }
+#define BDPT_DEF_ST256(name, hint)                                                                                          \
+  __device__ inline void name(float4* p, float4 a, float4 b) {                                                              \
+    asm volatile("st.global" hint ".v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"                                                \
+                 :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");      \
+  }
+BDPT_DEF_LD256(ld256_vtx, BDPT_HINT_VLD)
+BDPT_DEF_LD256(ld256_q, BDPT_HINT_QLD)
+BDPT_DEF_ST256(st256_vtx, BDPT_HINT_VST)
+BDPT_DEF_ST256(st256_q, BDPT_HINT_QST)
 // the 64-byte record of a vertex: {pos, material | n, D | alpha, S | wo, q}
 __device__ inline void store_vertex(const Job& J, size_t slot, float4 a, float4 b, float4 c, float4 e) {
-  st256(J.v0 + slot, a, b);
-  st256(J.v0 + slot + 2, c, e);
+  st256_vtx(J.v0 + slot, a, b);
+  st256_vtx(J.v0 + slot + 2, c, e);
 }
 
 // update_pixel (bidirection.cpp:544-551) without the lock: one 16-byte reduction per splat (REDG.E.ADD.F32x4, sm_90+)
@@ -346,7 +371,7 @@ struct Vtx {
 __device__ inline Vtx load_vtx(const Job& J, int kind, int j, int si) {
   size_t s = VSLOT(J, kind, j, si);
   float4 a, b, c, e;
-  ld256(J.v0 + s, &a, &b); ld256(J.v0 + s + 2, &c, &e);
+  ld256_vtx(J.v0 + s, &a, &b); ld256_vtx(J.v0 + s + 2, &c, &e);
   Vtx v;
   v.pos = mk3(a.x, a.y, a.z); v.mat = __float_as_int(a.w);
   v.n = mk3(b.x, b.y, b.z); v.D = b.w;
@@ -472,8 +497,8 @@ __global__ void __launch_bounds__(BDPT_CONNECT_NT, MINB) k_connect(const __grid_
     // stall samples: vertex -> its material -> the other vertex -> its material.)
     const bool needE = valid && t >= 2, needL = valid && s >= 1;
     float4 ea = make_float4(0.f, 0.f, 0.f, 0.f), eb = ea, ec = ea, ee = ea, la = ea, lb = ea, lc = ea, le = ea;
-    if (needE) { const float4* pe = J.v0 + VSLOT(J, 0, t, sj); ld256(pe, &ea, &eb); ld256(pe + 2, &ec, &ee); }
-    if (needL) { const float4* pl = J.v0 + VSLOT(J, 1, s >= 2 ? s : 1, sj); ld256(pl, &la, &lb); if (s >= 2) ld256(pl + 2, &lc, &le); }
+    if (needE) { const float4* pe = J.v0 + VSLOT(J, 0, t, sj); ld256_vtx(pe, &ea, &eb); ld256_vtx(pe + 2, &ec, &ee); }
+    if (needL) { const float4* pl = J.v0 + VSLOT(J, 1, s >= 2 ? s : 1, sj); ld256_vtx(pl, &la, &lb); if (s >= 2) ld256_vtx(pl + 2, &lc, &le); }
     E.mat = -1; E.D = 1.f; E.S = 0.f; E.q = 1.f; ME.type = -1; ML.type = -1;
     if (needE) {
       E.pos = mk3(ea.x, ea.y, ea.z); E.mat = __float_as_int(ea.w); E.n = mk3(eb.x, eb.y, eb.z); E.D = eb.w;
@@ -674,7 +699,7 @@ __global__ void __launch_bounds__(BDPT_CONNECT_NT, MINB) k_connect(const __grid_
         if (k_in >= J.seg_cap) J.qctr[4] = 1u;
         else {
           const size_t idx = (size_t)blockIdx.x * J.seg_cap + k_in;
-          st256(J.q0 + 2 * idx, make_float4(ve_pos.x, ve_pos.y, ve_pos.z, dist - BDPT_EPS_F),
+          st256_q(J.q0 + 2 * idx, make_float4(ve_pos.x, ve_pos.y, ve_pos.z, dist - BDPT_EPS_F),
                 make_float4(cdir.x, cdir.y, cdir.z, __uint_as_float(target)));
           J.q2[idx] = make_float4(ill.x, ill.y, ill.z, 0.f);
         }
@@ -816,7 +841,7 @@ __global__ void __launch_bounds__(128, MINB) k_shadow_pt(const Job J) {
     if (!wf.exhausted && (__popc(idle) >= FETCH || idle == 0xffffffffu)) {
       unsigned my = warp_fetch_chunk(J, nchunks, !active, wf);
       if (my != BDPT_NONE) {
-        float4 a, b; ld256(J.q0 + 2 * (size_t)my, &a, &b);
+        float4 a, b; ld256_q(J.q0 + 2 * (size_t)my, &a, &b);
         T.begin(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), BDPT_EPS_F, a.w);
         idx = my; active = true;
       }
@@ -976,6 +1001,25 @@ __global__ void k_tonemap(const float4* eye, const float4* light, int which, flo
     o[c] = (uint8_t)(g * 255.f);
   }
   o[3] = 255;
+}
+
+// End of a batch: the batch's splats (`batch`, the target of the kernels' reductions) are added to the frame's sums with
+// Kahan's compensated addition and the batch accumulators are zeroed.  An fp32 sum of N equal splats stops growing at
+// 2^24 of them; the one pixel that images a point light receives a splat from EVERY sample of the frame (8e8 at
+// 1024x768x1024 spp).  Inside a batch (<= 2^24 samples) the sums stay exact multiples of the splat; across batches the
+// compensation term keeps what the fp32 frame sum cannot hold, so its error stays at one rounding for any frame.
+__global__ void k_fold(float4* __restrict__ acc, float4* __restrict__ comp, float4* __restrict__ batch, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 b = batch[i];
+  if (b.x == 0.f && b.y == 0.f && b.z == 0.f) return;   // pixel untouched by this batch (NaN compares false: folded)
+  float4 a = acc[i], c = comp[i];
+  float y, t;
+  y = b.x - c.x; t = a.x + y; c.x = (t - a.x) - y; a.x = t;
+  y = b.y - c.y; t = a.y + y; c.y = (t - a.y) - y; a.y = t;
+  y = b.z - c.z; t = a.z + y; c.z = (t - a.z) - y; a.z = t;
+  acc[i] = a; comp[i] = c;
+  batch[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // RGBA-padded accumulators -> the W*H*3 image the caller reads, divided by ns

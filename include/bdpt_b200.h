@@ -123,7 +123,10 @@ int bdpt_read_framebuffer(BdptContext* ctx, int which, float* rgb_out); /* D2H, 
 /* Device pointer to the un-normalised fp32 accumulators so that a multi-GPU caller can reduce them in place before
  * reading.  They are ONE allocation of 2*W*H pixels of 4 floats {r, g, b, unused}: the eye image, then the light
  * image.  which = BDPT_BUFFER_EYE / BDPT_BUFFER_LIGHT: that image (W*H*4 floats); BDPT_BUFFER_SUM: the whole
- * allocation (2*W*H*4 floats) — what a single ncclReduce / torch.distributed.reduce sums (bdpt_reduce does that). */
+ * allocation (2*W*H*4 floats) — what a single ncclReduce / torch.distributed.reduce sums (bdpt_reduce does that).
+ * These are the frame's sums as of the last finished bdpt_render: the kernels splat into per-batch accumulators that a
+ * compensated (Kahan) addition folds into them after every batch, so a pixel that receives a splat from every sample of
+ * the frame (the image of a point light) does not stop growing at 2^24 splats as a plain fp32 sum would. */
 int bdpt_framebuffer_device(BdptContext* ctx, int which, void** device_ptr, size_t* n_floats);
 /* toColor (util/image.h:194-209): exposure sqrt(2), gamma 2.2, clamp, RGBA8, row 0 = TOP as PNGs want
  * (RaytracedRenderer::save_image flips, raytraced_renderer.cpp:690-728). */

@@ -700,6 +700,27 @@ def test_balance_heuristic_matches_oracle(api, O):
     assert abs(a.framebuffer(0).mean() - b.framebuffer(0).mean()) <= 1e-2 * b.framebuffer(0).mean()
 
 
+def test_point_light_pixel_keeps_its_bits_over_many_batches(api):
+    """Every sample of a frame splats its (t=1, s=1) connection of a point light onto ONE pixel of the light image: 1.4e9
+    equal splats here (480 x 360: smaller frames of this camera do not see the light).  A plain fp32 sum stops growing at 2^24 of them (2^24 x the 16 a half-warp merges = 2.7e8); the
+    batch accumulators + compensated fold (k_fold) keep the frame's sum right.  Known answer: the same frame rendered
+    as 64 separate shards, each read back and summed in fp64 on the host."""
+    W, H, ns, m, shards = 480, 360, 8192, 2, 64
+    R = make_renderer(api, "CBempty", W, H, ns_aa=ns, max_ray_depth=m, seed=4)
+    R.render()
+    assert R.stats()["n_batches"] >= 40
+    whole = R.framebuffer(api.BUFFER_LIGHT).astype(np.float64)
+    parts = np.zeros_like(whole)
+    for k in range(shards):
+        R.clear()
+        R.render(first_sample=k * (ns // shards), n_samples=ns // shards)
+        parts += R.framebuffer(api.BUFFER_LIGHT).astype(np.float64)
+    y, x = np.unravel_index(np.argmax(parts[..., 1]), parts.shape[:2])
+    assert parts[y, x, 1] > 100 * np.median(parts[..., 1])          # the pixel that images the light
+    assert abs(whole[y, x, 1] - parts[y, x, 1]) <= 1e-6 * parts[y, x, 1]
+    assert np.allclose(whole, parts, rtol=1e-4, atol=1e-7)
+
+
 def test_accumulators_are_one_allocation(api):
     """What the single reduce of a multi-GPU frame sums: eye image then light image, W*H*4 floats each, contiguous."""
     R = make_renderer(api, "CBspheres_lambertian", 40, 30, ns_aa=2, max_ray_depth=3)
