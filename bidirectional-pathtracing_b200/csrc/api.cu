@@ -535,6 +535,11 @@ int bdpt_create(int device, BdptContext** out) {
   if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return BDPT_ERR_CUDA; }
   ctx->own_stream = true;
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  // (measurement only: the L1 / shared-memory split the driver picks for kernels that use almost no shared memory)
+  if (const char* e = getenv("BDPT_CACHE_CONFIG")) {
+    const int c = atoi(e);
+    cudaDeviceSetCacheConfig(c == 1 ? cudaFuncCachePreferL1 : c == 2 ? cudaFuncCachePreferShared : c == 3 ? cudaFuncCachePreferEqual : cudaFuncCachePreferNone);
+  }
   if (const char* e = getenv("BDPT_SCHED")) ctx->sched_req = std::min(1, atoi(e));
   ctx->sched = ctx->sched_req >= 0 ? ctx->sched_req : 1;
   if (const char* e = getenv("BDPT_BATCH_LOG2")) ctx->batch_log2 = std::min(24, std::max(10, atoi(e)));
