@@ -98,6 +98,12 @@ __device__ inline bool decode_sample(const Job& J, unsigned long long g, int* x,
 //   vertex loads  (k_connect)    L1::no_allocate                     connect -1.8 % (with L2::evict_first: +4.4 %, the kernel's own L2 prefetch is lost)
 //   queue stores  (k_connect)    L1::no_allocate + L2::evict_first   connect -0.9 %
 //   queue loads   (k_shadow_pt)  L1::no_allocate
+#ifndef BDPT_SHADOW_PF_SPLAT
+#define BDPT_SHADOW_PF_SPLAT 0
+#endif
+#ifndef BDPT_SHADOW_PF_NEXT
+#define BDPT_SHADOW_PF_NEXT 32
+#endif
 #ifndef BDPT_HINT_VST
 #define BDPT_HINT_VST ".L1::no_allocate.L2::evict_first"
 #endif
@@ -699,9 +705,10 @@ __global__ void __launch_bounds__(BDPT_CONNECT_NT, MINB) k_connect(const __grid_
         if (k_in >= J.seg_cap) J.qctr[4] = 1u;
         else {
           const size_t idx = (size_t)blockIdx.x * J.seg_cap + k_in;
+          // (the pixel travels with the contribution: the splat then needs one 16-byte load, not two)
           st256_q(J.q0 + 2 * idx, make_float4(ve_pos.x, ve_pos.y, ve_pos.z, dist - BDPT_EPS_F),
-                make_float4(cdir.x, cdir.y, cdir.z, __uint_as_float(target)));
-          J.q2[idx] = make_float4(ill.x, ill.y, ill.z, 0.f);
+                make_float4(cdir.x, cdir.y, cdir.z, 0.f));
+          J.q2[idx] = make_float4(ill.x, ill.y, ill.z, __uint_as_float(target));
         }
       }
     }
@@ -731,7 +738,7 @@ __global__ void __launch_bounds__(BDPT_CONNECT_NT, MINB) k_connect(const __grid_
 // reduction.
 __device__ inline void shadow_splat(const Job& J, unsigned mask, unsigned idx) {
   const float4 c = J.q2[idx];
-  const unsigned int tg = __float_as_uint(J.q0[2 * (size_t)idx + 1].w);
+  const unsigned int tg = __float_as_uint(c.w);
   float sx = c.x, sy = c.y, sz = c.z;
   if (J.point_lights) {
     const unsigned li = __ballot_sync(mask, (tg & 0x80000000u) != 0u);
@@ -807,6 +814,10 @@ __device__ inline unsigned warp_fetch_chunk(const Job& J, unsigned nchunks, bool
   const unsigned my = wf.next + __popc(mask & ((1u << lane) - 1u));
   const bool got = want && my < wf.end;
   wf.next = min(wf.next + (unsigned)__popc(mask), wf.end);
+#if BDPT_SHADOW_PF_NEXT
+  // the entries the NEXT hand-out will give away: into L1 now (BDPT_SHADOW_PF_NEXT of them, 32 B each)
+  if (lane < BDPT_SHADOW_PF_NEXT && wf.next + lane < wf.end) asm volatile("prefetch.global.L1 [%0];" :: "l"(J.q0 + 2 * (size_t)(wf.next + lane)));
+#endif
   return got ? my : BDPT_NONE;
 }
 
@@ -856,6 +867,9 @@ __global__ void __launch_bounds__(128, MINB) k_shadow_pt(const Job J) {
       if (T.hit.leaf < 0) {
         if (pend != BDPT_NONE) shadow_splat(J, 1u << (threadIdx.x & 31), pend);   // the slot is taken: this lane cannot wait
         pend = idx;
+#if BDPT_SHADOW_PF_SPLAT
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(J.q2 + idx));   // the contribution, wanted a few rounds from now
+#endif
       }
     }
   }
