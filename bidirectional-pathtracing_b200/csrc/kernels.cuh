@@ -827,9 +827,17 @@ __device__ inline void stage_top_nodes(const Job& J, uint4* top) {
   __syncthreads();
 }
 
-// FETCH: idle lanes a warp tolerates before it fetches (measured 4: 6.53, 8: 6.31, 12: 6.22, 16: 6.24 ms per 2^24
-// samples); SPLAT: parked rays it collects before it splats (8: 6.62, 16: 6.53, 24: 6.70 at FETCH = 4).
-template <int MINB, int TR = 0, int FETCH = 12, int SPLAT = 16>
+// FETCH: idle lanes a warp tolerates before it fetches; SPLAT: parked rays it collects before it splats.  Round 1
+// (6.2 ms kernel): FETCH 4: 6.53, 8: 6.31, 12: 6.22, 16: 6.24 ms per 2^24 samples; SPLAT 8: 6.62, 16: 6.53, 24: 6.70.
+// Re-measured on the 4.75 ms kernel (PLOC tree, one-load splats, L1-prefetched hand-outs), CBbunny4: FETCH 8: 4.734,
+// 12: 4.755, 16: 4.93; SPLAT 12: 4.732, 16: 4.755, 22: 4.81.
+#ifndef BDPT_SHADOW_FT
+#define BDPT_SHADOW_FT 8
+#endif
+#ifndef BDPT_SHADOW_SP
+#define BDPT_SHADOW_SP 12
+#endif
+template <int MINB, int TR = 0, int FETCH = BDPT_SHADOW_FT, int SPLAT = BDPT_SHADOW_SP>
 __global__ void __launch_bounds__(128, MINB) k_shadow_pt(const Job J) {
   extern __shared__ uint4 top[];
   stage_top_nodes(J, top);
@@ -910,6 +918,8 @@ __global__ void __launch_bounds__(128, MINB) k_walk_pt(const __grid_constant__ J
     }
     if (__ballot_sync(0xffffffffu, phase != 0) == 0u && wf.exhausted) break;
     if (phase == 1) {
+      // (requesting the winner's normals and fp64 geometry into L1 here, for the shading that follows a few rounds later —
+      // three prefetch.global.L1 per ray — made the walk 37 % slower)
       if (T.step<false, TR>(J.sc, stack, top, (uint32_t)J.ntop)) { phase = 2; nrays++; }
     }
   }
