@@ -98,9 +98,6 @@ __device__ inline bool decode_sample(const Job& J, unsigned long long g, int* x,
 //   vertex loads  (k_connect)    L1::no_allocate                     connect -1.8 % (with L2::evict_first: +4.4 %, the kernel's own L2 prefetch is lost)
 //   queue stores  (k_connect)    L1::no_allocate + L2::evict_first   connect -0.9 %
 //   queue loads   (k_shadow_pt)  L1::no_allocate
-#ifndef BDPT_SHADOW_PF_SPLAT
-#define BDPT_SHADOW_PF_SPLAT 0
-#endif
 #ifndef BDPT_SHADOW_PF_NEXT
 #define BDPT_SHADOW_PF_NEXT 32
 #endif
@@ -875,9 +872,6 @@ __global__ void __launch_bounds__(128, MINB) k_shadow_pt(const Job J) {
       if (T.hit.leaf < 0) {
         if (pend != BDPT_NONE) shadow_splat(J, 1u << (threadIdx.x & 31), pend);   // the slot is taken: this lane cannot wait
         pend = idx;
-#if BDPT_SHADOW_PF_SPLAT
-        asm volatile("prefetch.global.L1 [%0];" :: "l"(J.q2 + idx));   // the contribution, wanted a few rounds from now
-#endif
       }
     }
   }
