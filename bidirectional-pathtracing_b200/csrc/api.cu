@@ -122,9 +122,11 @@ struct BdptContext {
   int point_lights = 0; // the uploaded scene has a point light
   int spec = 7;         // which kernels may use their trait-specialised build: 1 walk, 2 connect, 4 shadow (BDPT_SPEC, tuning only)
   // batch size cap (samples) and its memory budget (BDPT_BATCH_LOG2, BDPT_BATCH_GIB).  The persistent kernels end
-  // with a tail of long paths; at 2^24 samples per batch that tail is ~1 % of the step (2^22: ~4 %), and 48 of the
-  // 180 GB are there to be used.  Storage is only ever allocated for the samples a render actually has.
-  int batch_log2 = 24, batch_gib = 48;
+  // with a tail of long paths and every batch starts with cold caches: CBbunny4 at 2^22 / 2^23 / 2^24 / 2^25 samples per
+  // batch renders 927 / 966 / 988 / 999 M samples/s, and at m = 16 (16 KB per sample: the budget binds, not the cap)
+  // CBgems gains 4 % from 48 -> 96 GiB.  96 of the 180 GB are there to be used; storage is only ever allocated for
+  // the samples a render actually has, and a device that cannot give it gets a smaller batch (bdpt_render).
+  int batch_log2 = 25, batch_gib = 96;
   int walk_ctas = BDPT_WALK_MINB, shadow_ctas = 0;  // resident CTAs per SM of the persistent kernels (shadow: 0 = the build's own, 9 or 8)
   // multi-GPU (comm.inc): an ncclComm_t, bound at run time
   void* comm = nullptr; int comm_ranks = 0, comm_rank = 0;
@@ -542,8 +544,8 @@ int bdpt_create(int device, BdptContext** out) {
   }
   if (const char* e = getenv("BDPT_SCHED")) ctx->sched_req = std::min(1, atoi(e));
   ctx->sched = ctx->sched_req >= 0 ? ctx->sched_req : 1;
-  if (const char* e = getenv("BDPT_BATCH_LOG2")) ctx->batch_log2 = std::min(24, std::max(10, atoi(e)));
-  if (const char* e = getenv("BDPT_BATCH_GIB")) ctx->batch_gib = std::min(64, std::max(1, atoi(e)));
+  if (const char* e = getenv("BDPT_BATCH_LOG2")) ctx->batch_log2 = std::min(26, std::max(10, atoi(e)));
+  if (const char* e = getenv("BDPT_BATCH_GIB")) ctx->batch_gib = std::min(144, std::max(1, atoi(e)));
   if (const char* e = getenv("BDPT_TOP_NODES")) ctx->top_nodes = std::max(0, std::min(512, atoi(e)));
   if (const char* e = getenv("BDPT_CONNECT_MINB")) ctx->connect_minb = atoi(e);
   if (const char* e = getenv("BDPT_SPEC")) ctx->spec = atoi(e);
@@ -823,6 +825,8 @@ int bdpt_render(BdptContext* ctx, const BdptRenderParams* p) {
   const size_t per_sample = (size_t)2 * (m + 1) * 64 + (size_t)(m + 1) * (m + 1) * 48 + 8;
   size_t B = (size_t)((size_t)ctx->batch_gib << 30) / per_sample;
   B = std::min<size_t>(B, (size_t)1 << ctx->batch_log2);
+  // a point light's pixel takes one splat per sample: its batch sum stays an exact multiple of the splat up to 2^24 (k_fold)
+  if (ctx->point_lights) B = std::min<size_t>(B, (size_t)1 << 24);
   B = std::max<size_t>(B & ~(size_t)1023, 1024);
   const int cw = ctx->cell[2] > 0 ? ctx->cell[2] : ctx->W, ch = ctx->cell[2] > 0 ? ctx->cell[3] : ctx->H;
   const int tiles_x = (cw + 7) / 8, npix_pad = tiles_x * ((ch + 3) / 4) * 32;

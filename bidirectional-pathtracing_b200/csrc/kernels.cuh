@@ -1024,7 +1024,7 @@ __global__ void k_tonemap(const float4* eye, const float4* light, int which, flo
 // End of a batch: the batch's splats (`batch`, the target of the kernels' reductions) are added to the frame's sums with
 // Kahan's compensated addition and the batch accumulators are zeroed.  An fp32 sum of N equal splats stops growing at
 // 2^24 of them; the one pixel that images a point light receives a splat from EVERY sample of the frame (8e8 at
-// 1024x768x1024 spp).  Inside a batch (<= 2^24 samples) the sums stay exact multiples of the splat; across batches the
+// 1024x768x1024 spp).  Inside a batch (<= 2^24 samples where a point light exists: api.cu) the sums stay exact multiples of the splat; across batches the
 // compensation term keeps what the fp32 frame sum cannot hold, so its error stays at one rounding for any frame.
 __global__ void k_fold(float4* __restrict__ acc, float4* __restrict__ comp, float4* __restrict__ batch, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
